@@ -1,0 +1,53 @@
+// Internal (non-ABI) prototypes shared between the translation units of libppoaf_b200.so.
+#pragma once
+#include "common.cuh"
+
+namespace ppoaf {
+
+// mlp.cu
+void linear_forward(const float* X, int ldx, const int64_t* idx, const int32_t* cursor, int cursor_stride,
+                    const float* W, const float* b, float* Y, int rows, int in, int out, int act, cudaStream_t s);
+void linear_backward_x(const float* dZ, const float* W, const float* Xact, float* dX, int rows, int in, int out,
+                       int act, cudaStream_t s);
+void linear_backward_w(const float* dZ, const float* X, int ldx, const int64_t* idx, const int32_t* cursor,
+                       int cursor_stride, float* dW, float* db, int rows, int in, int out, cudaStream_t s);
+int64_t param_layout(const ppoaf_mlp_desc* net, int32_t log_std_dim, int64_t* offsets);
+int check_mlp_desc(const ppoaf_mlp_desc* net, const char* who);
+
+// loss.cu
+struct LossArgs {
+    const float* actor_out;      // [batch, pred]  mean (Gaussian) or logits (Categorical)
+    const float* critic_out;     // [batch]
+    const float* log_std;        // [act_dim] (Gaussian)
+    const void* raw_actions;     // dataset [N, act_dim] fp32 or int64
+    const float* advantages;     // dataset [N]
+    const float* log_probs;      // dataset [N]
+    const float* rewards_to_go;  // dataset [N]
+    float* values;               // dataset [N] (scatter target)
+    const int64_t* perm;
+    const int32_t* cursor;
+    int batch_size;              // cursor stride
+    int batch;                   // rows in this minibatch
+    const float* mb_adv_stats;
+    const float* mb_val_stats;
+    const double* hparams;
+    double* epoch_stats;
+    float* d_actor_out;          // [batch, pred]
+    float* d_critic_out;         // [batch]  (or [2, batch] scratch when vf_clip is on)
+    float* d_log_std;            // [act_dim] inside grads
+    float* partials;             // workspace: [n_blocks, kLossScalars + act_dim]
+    unsigned int* ticket;        // zero-initialised, self-resetting
+    int head, act_dim, pred_dim;
+    int use_huber, normalize_adv, normalize_values, vf_clip_enabled;
+    float min_std;
+};
+size_t loss_workspace_bytes(int max_batch, int act_dim);
+int launch_ppo_loss(const LossArgs& a, cudaStream_t s);
+
+// optim.cu
+size_t optim_workspace_bytes(int64_t n_total);
+int launch_advance_cursor(int32_t* mb_cursor, cudaStream_t s);
+int launch_clip_adam(float* params, const float* grads, float* m, float* v, int64_t* adam_step, int32_t* mb_cursor,
+                     const double* hparams, int64_t n_actor, int64_t n_critic, void* workspace, cudaStream_t s);
+
+}  // namespace ppoaf

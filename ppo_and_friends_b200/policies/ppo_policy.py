@@ -1,0 +1,301 @@
+"""
+PPOPolicy for the B200 path: the reference class's trainer-facing surface
+(policies/ppo_policy.py:25-1419) with the hot half re-implemented on device.
+
+Kept (same names, argument meaning, error text): constructor hyper-parameters (:33-300),
+`register_agent`, `finalize` (:302-345), `initialize_episodes` (:474-504), `initialize_dataset`
+(:506-526), `add_episode_info` (:545-651), `end_episodes` (:653-712), `finalize_dataset` (:714-719),
+`clear_dataset` (:721-727), `evaluate` (:891-952), `get_critic_values` (:1057-1071),
+`update_learning_rate` (:1073-1084), `get_bs_clip_range` (:1086-1112), attributes `actor`, `critic`,
+`actor_optim`, `critic_optim`, `dataset`, `surr_clip`, `vf_clip`, `entropy_weight()`, `lr()`,
+`kl_loss_weight`, `target_kl`, `use_huber_loss`, `using_lstm`, `frozen`, `enable_icm`.
+
+Changed on purpose: there are no per-segment EpisodeInfo objects and no autograd.  The rollout goes
+into a packed device ring, segments into a table, and `update_weights(actor_loss, critic_loss)` has
+no counterpart because the losses never exist as tensors — the fused step in ppo.py
+(`ppo_batch_train`) replaces `PPO._ppo_batch_train` + `evaluate` + `update_weights` as one unit.
+Out of scope (raise): LSTM networks, ICM, MAT, Bernoulli/MultiCategorical/Mixed action heads.
+"""
+import numpy as np
+import torch
+
+from .. import _lib, ops
+from ..networks.feed_forward import PolicyNetworks, _AdamView, hidden_sizes
+from ..utils.episode_info import PPODataset, RolloutRing
+from ..utils.misc import update_optimizer_lr
+from ..utils.mpi_utils import abort, barrier, broadcast_model_parameters, rank_print
+
+
+class CallableValue:
+    """utils/schedulers.py:11-29: a constant that looks like a scheduler."""
+
+    def __init__(self, value):
+        self.value = value
+
+    def finalize(self, status_dict):
+        pass
+
+    def __call__(self):
+        return self.value
+
+
+def _as_callable(v):
+    return v if callable(v) else CallableValue(v)
+
+
+def space_dtype_str(space):
+    """utils/misc.py:17-46, duck-typed so gymnasium itself is not required."""
+    if hasattr(space, "spaces"):
+        return "mixed"
+    dt = np.dtype(getattr(space, "dtype", np.float32))
+    if np.issubdtype(dt, np.floating):
+        return "continuous"
+    if np.issubdtype(dt, np.integer):
+        name = type(space).__name__
+        if name == "Discrete" or (hasattr(space, "n") and not hasattr(space, "nvec") and tuple(getattr(space, "shape", ())) == ()):
+            return "discrete"
+        if name == "MultiBinary":
+            return "multi-binary"
+        if name == "MultiDiscrete" or hasattr(space, "nvec"):
+            return "multi-discrete"
+    return "unknown"
+
+
+def _flat_dim(space):
+    shape = tuple(getattr(space, "shape", ()) or ())
+    return int(np.prod(shape)) if len(shape) else 1
+
+
+class PPOPolicy:
+
+    def __init__(self, name, action_space, actor_observation_space, critic_observation_space, envs_per_proc,
+                 bootstrap_clip=(-100., 100.), ac_network=None, actor_kw_args={}, critic_kw_args={}, icm_kw_args={},
+                 target_kl=100., surr_clip=0.2, vf_clip=None, gradient_clip=0.5, lr=3e-4, icm_lr=3e-4,
+                 entropy_weight=0.01, kl_loss_weight=0.0, use_gae=True, gamma=0.99, lambd=0.95,
+                 dynamic_bs_clip=False, enable_icm=False, agent_shared_icm=False, icm_network=None,
+                 intr_reward_weight=1.0, icm_beta=0.8, use_huber_loss=False, test_mode=False, verbose=False,
+                 **kw_args):
+        if enable_icm:
+            abort("ERROR: ICM is outside the B200 update path (SURVEY.md §2 row 11).")
+        self.name = name
+        self.action_space = action_space
+        self.actor_obs_space = actor_observation_space
+        self.critic_obs_space = critic_observation_space
+        self.enable_icm = False
+        self.test_mode = test_mode
+        self.use_gae, self.gamma, self.lambd = use_gae, gamma, lambd
+        self.dynamic_bs_clip = dynamic_bs_clip
+        self.using_lstm = False
+        self.dataset = None
+        self.device = torch.device("cpu")
+        self.agent_ids = np.array([])
+        self.target_kl, self.surr_clip, self.vf_clip = target_kl, surr_clip, vf_clip
+        self.gradient_clip, self.kl_loss_weight = gradient_clip, kl_loss_weight
+        self.envs_per_proc = envs_per_proc
+        self.agent_grouping = False
+        self.verbose = verbose
+        self.use_huber_loss = use_huber_loss
+        self.frozen = False
+        self.lr = _as_callable(lr)
+        self.entropy_weight = _as_callable(entropy_weight)
+
+        self.action_dtype = space_dtype_str(action_space)
+        if self.action_dtype == "unknown":
+            abort(f"ERROR: unknown action type: {type(action_space)} with dtype {getattr(action_space, 'dtype', None)}.")
+        if self.action_dtype not in ("continuous", "discrete"):
+            abort(f"ERROR: {self.action_dtype} action heads are outside the B200 update path "
+                  "(Gaussian and Categorical only, SURVEY.md §2 row 8).")
+        rank_print("{} policy using {} actions.".format(self.name, self.action_dtype))
+
+        self.have_bootstrap_clip = bootstrap_clip is not None
+        if self.have_bootstrap_clip:
+            self.bootstrap_clip = (_as_callable(bootstrap_clip[0]), _as_callable(bootstrap_clip[1]))
+        else:
+            self.bootstrap_clip = None
+
+        if self.action_dtype == "discrete":
+            self.action_dim = 1
+            self.action_pred_size = int(action_space.n)
+        else:
+            self.action_dim = _flat_dim(action_space)
+            self.action_pred_size = self.action_dim
+        self.actor_kw_args = dict(actor_kw_args)
+        self.critic_kw_args = dict(critic_kw_args)
+        self._ring = None
+        self._engine = None
+
+    # ------------------------------------------------------------------------------------------------
+    def register_agent(self, agent_id):
+        """ppo_policy.py:352-362 (set union, so the order is not insertion order)."""
+        self.agent_ids = np.array(list(set(self.agent_ids).union({agent_id})))
+
+    def finalize(self, status_dict, device):
+        self.device = torch.device(device)
+        _lib.require_cuda()
+        ops.runtime_init()
+        self.agent_idxs = np.arange(len(self.agent_ids))
+        self.num_agents = self.agent_idxs.size
+        self._agent_col = {a: i for i, a in enumerate(self.agent_ids)}
+        self._initialize_networks()
+        for sched in (self.lr, self.entropy_weight):
+            sched.finalize(status_dict)
+        if self.have_bootstrap_clip:
+            self.bootstrap_clip[0].finalize(status_dict)
+            self.bootstrap_clip[1].finalize(status_dict)
+        self.actor_optim = _AdamView(self.lr())
+        self.critic_optim = _AdamView(self.lr())
+        self.icm_optim = None
+
+    def _initialize_networks(self):
+        """ppo_policy.py:390-472: actor then critic, broadcast from rank 0."""
+        gaussian = self.action_dtype == "continuous"
+        akw, ckw = self.actor_kw_args, self.critic_kw_args
+        a_hidden = hidden_sizes(akw.get("hidden_size", 128), akw.get("hidden_depth", 3))
+        c_hidden = hidden_sizes(ckw.get("hidden_size", 128), ckw.get("hidden_depth", 3))
+        do, dc = _flat_dim(self.actor_obs_space), _flat_dim(self.critic_obs_space)
+        self.min_std = float(akw.get("min_std", 0.01))
+        self.nets = PolicyNetworks(
+            self.device, [do] + a_hidden + [self.action_pred_size], [dc] + c_hidden + [1],
+            akw.get("activation", torch.nn.ReLU()), ckw.get("activation", torch.nn.ReLU()), gaussian,
+            self.action_dim, std_offset=akw.get("std_offset", 0.5))
+        self.actor, self.critic = self.nets.actor, self.nets.critic
+        if gaussian:
+            lo = akw.get("distribution_min", getattr(self.action_space, "low", -1.0))
+            hi = akw.get("distribution_max", getattr(self.action_space, "high", 1.0))
+            self.dist_min = np.asarray(lo, dtype=np.float32).reshape(-1)
+            self.dist_max = np.asarray(hi, dtype=np.float32).reshape(-1)
+            if np.isinf(self.dist_min).any() or np.isinf(self.dist_max).any():
+                abort("ERROR: the gaussian distribution min/max must not be inf; set "
+                      "actor_kw_args['distribution_min'/'distribution_max'].")
+        broadcast_model_parameters(self.nets.flat_params)
+        barrier()
+
+    @property
+    def head(self):
+        return _lib.HEAD_GAUSSIAN_TANH if self.action_dtype == "continuous" else _lib.HEAD_CATEGORICAL
+
+    def to(self, device):
+        self.device = torch.device(device)
+
+    def train(self):
+        pass
+
+    def eval(self):
+        pass
+
+    # -- A0: dataset / episode lifecycle ----------------------------------------------------------------
+    def initialize_episodes(self, env_batch_size, status_dict):
+        E = int(env_batch_size)
+        if self._ring is None or self._ring.E != E or self._ring.A != len(self.agent_ids):
+            self._ring = RolloutRing(self.device, E, len(self.agent_ids), _flat_dim(self.actor_obs_space),
+                                     _flat_dim(self.critic_obs_space), self.action_dim,
+                                     self.action_dtype == "discrete",
+                                     capacity_steps=max(64, getattr(self, "rollout_steps_hint", 64)))
+        self._ring.reset()
+        if self.dataset is not None:
+            self.dataset.ring = self._ring
+        A = len(self.agent_ids)
+        self._open_t0 = np.zeros((A, E), dtype=np.int64)        # ring step where the open segment began
+        self._open_start_ts = np.zeros((A, E), dtype=np.int64)  # EpisodeInfo.starting_ts of the open segment
+        clip = self.get_bs_clip_range(None)
+        self._open_clip = np.empty((A, E, 2), dtype=np.float64)
+        self._open_clip[:] = (np.nan, np.nan) if clip is None else clip
+
+    def initialize_dataset(self):
+        self.dataset = PPODataset(self.device, self.action_dtype, sequence_length=1, ring=self._ring,
+                                  use_gae=self.use_gae, gamma=self.gamma, lambd=self.lambd)
+
+    def validate_agent_id(self, agent_id):
+        if agent_id not in self._agent_col:
+            abort(f"ERROR: agent {agent_id} has not been registered with policy {self.name}. "
+                  "Make sure that you've set up your policies correctly.")
+
+    # -- A1 ------------------------------------------------------------------------------------------------
+    def add_episode_info(self, agent_id, critic_observations, observations, next_observations, raw_actions,
+                         actions, values, log_probs, rewards, where_done):
+        self.validate_agent_id(agent_id)
+        self._ring.add_step(self._agent_col[agent_id], critic_observations, observations, next_observations,
+                            raw_actions, actions, values, log_probs, rewards)
+
+    # -- A2 ------------------------------------------------------------------------------------------------
+    def end_episodes(self, agent_id, env_idxs, episode_lengths, terminal, ending_values, ending_rewards):
+        if self.frozen:
+            return
+        self.validate_agent_id(agent_id)
+        a = self._agent_col[agent_id]
+        ring = self._ring
+        t_now = int(ring.steps[a])
+        ev = _host(ending_values)
+        er = _host(ending_rewards)
+        for idx, env_i in enumerate(env_idxs):
+            env_i = int(env_i)
+            ending_ts = int(episode_lengths[env_i])
+            t0 = int(self._open_t0[a, env_i])
+            length = t_now - t0
+            # bootstrap arrays are indexed by POSITION in env_idxs, exactly like the reference
+            # (ppo_policy.py:684-689)
+            ending_value = float(ev[idx])
+            ending_reward = float(er[idx])
+            clip = self._open_clip[a, env_i]
+            if self.have_bootstrap_clip:
+                ending_reward = float(np.clip(ending_reward, clip[0], clip[1]))   # episode_info.py:450-454
+            col = a * ring.E + env_i
+            self.dataset.add_segment(col, t0, length, bool(terminal[idx]), ending_value, ending_reward,
+                                     int(self._open_start_ts[a, env_i]), ending_ts)
+            if self.have_bootstrap_clip:
+                if self.dynamic_bs_clip:
+                    seg_r = ring.segment_rewards(col, t0, length)
+                    self._open_clip[a, env_i] = (float(seg_r.min()), float(seg_r.max()))
+                else:
+                    self._open_clip[a, env_i] = self.get_bs_clip_range(None)
+            self._open_start_ts[a, env_i] = 0 if terminal[idx] else ending_ts
+            self._open_t0[a, env_i] = t_now
+
+    def finalize_dataset(self):
+        self.dataset.build()
+
+    def clear_dataset(self):
+        self.dataset = None
+
+    def get_bs_clip_range(self, ep_rewards):
+        if not self.have_bootstrap_clip:
+            return None
+        if self.dynamic_bs_clip and ep_rewards is not None:
+            return (min(ep_rewards), max(ep_rewards))
+        return (self.bootstrap_clip[0](), self.bootstrap_clip[1]())
+
+    # -- P1: forward-only evaluation (also what rollout-time inference builds on) ---------------------------
+    def evaluate(self, batch_critic_obs, batch_obs, batch_actions):
+        """(values, log_probs, entropy) for a batch, through the CUDA MLP + head kernels."""
+        values = self.critic(batch_critic_obs).reshape(-1)
+        pred = self.actor(batch_obs)
+        acts = batch_actions if torch.is_tensor(batch_actions) else torch.as_tensor(np.asarray(batch_actions))
+        if self.action_dtype == "continuous":
+            acts = acts.to(self.device, torch.float32).reshape(pred.shape[0], -1).contiguous()
+            log_std = self.actor.state_dict()["distribution.log_std"]
+        else:
+            acts = acts.to(self.device, torch.int64).reshape(pred.shape[0], -1).contiguous()
+            log_std = None
+        lp, ent = ops.head_evaluate(self.head, pred, log_std, acts, self.min_std)
+        return values, lp, ent
+
+    def get_critic_values(self, obs):
+        return self.critic(obs)
+
+    def update_weights(self, actor_loss, critic_loss):
+        raise _lib.PpoafError(
+            "PPOPolicy.update_weights(actor_loss, critic_loss) has no counterpart on the B200 path: losses are "
+            "never materialised as autograd tensors. Use ppo_and_friends_b200.ppo.ppo_batch_train, which replaces "
+            "PPO._ppo_batch_train + evaluate + update_weights as one fused step.")
+
+    def update_learning_rate(self):
+        if self.frozen:
+            return
+        update_optimizer_lr(self.actor_optim, self.lr())
+        update_optimizer_lr(self.critic_optim, self.lr())
+
+
+def _host(x):
+    if torch.is_tensor(x):
+        return x.detach().cpu().numpy().reshape(-1)
+    return np.asarray(x).reshape(-1)

@@ -1,0 +1,273 @@
+"""
+The PPO update loop on the B200 path: replaces `PPO._ppo_batch_train` (reference ppo.py:2274-2485)
+and the DataLoader / epoch / KL-early-stop section of `PPO.learn` (ppo.py:2178-2238).
+
+`ppo_batch_train(ppo, data_loader, policy_id)` keeps the reference's signature and side effects
+(`status_dict[policy_id]["actor loss" | "critic loss" | "kl avg" | "weighted entropy"]`,
+`dataset.values` overwritten, value-normaliser statistics advanced on every minibatch), but one
+epoch is: draw the permutation with the reference's RNG protocol on the host -> one small prepare
+kernel -> a replayed CUDA graph per minibatch (gather + actor/critic forward + fused loss +
+backward [+ NCCL all-reduce of the flat gradient] + clip + Adam) -> ONE host sync to read the five
+epoch scalars.  Hyper-parameters live in a device block that is refreshed per epoch, so
+schedulers keep working without re-capturing.
+"""
+import ctypes as C
+import os
+from collections import OrderedDict
+
+import numpy as np
+import torch
+
+from . import _lib, ops
+from ._lib import HP, ST, check, load, ptr, stream_ptr
+from .utils import mpi_utils
+from .utils.misc import RunningStatNormalizer
+
+
+def draw_minibatch_permutation(n):
+    """
+    The permutation `for batch in DataLoader(dataset, batch_size, shuffle=True)` would use, drawn
+    from torch's GLOBAL CPU generator with the same calls in the same order (torch
+    utils/data/dataloader.py:705-710 draws the base seed; sampler.py:160-185 draws the seed of a
+    private generator and calls randperm) — so minibatch indices are bit-identical to the reference
+    for a given `torch.manual_seed` (the CLI seeds rank r with seed + r, ppoaf_cli.py:419).
+    """
+    _base_seed = torch.empty((), dtype=torch.int64).random_().item()
+    seed = int(torch.empty((), dtype=torch.int64).random_().item())
+    g = torch.Generator()
+    g.manual_seed(seed)
+    return torch.randperm(n, generator=g)
+
+
+class UpdateEngine:
+    """Per-policy device state of the fused update (buffers, config structs, captured graphs)."""
+
+    def __init__(self, policy, batch_size, normalize_adv=True, normalize_values=True, value_normalizer=None,
+                 use_graphs=None):
+        _lib.require_cuda()
+        self.policy = policy
+        self.device = policy.device
+        self.batch_size = int(batch_size)
+        self.normalize_adv = bool(normalize_adv)
+        self.normalize_values = bool(normalize_values)
+        self.value_normalizer = value_normalizer
+        self.use_graphs = (os.environ.get("PPOAF_NO_GRAPH", "0") != "1") if use_graphs is None else use_graphs
+        nets = policy.nets
+        cfg = _lib.UpdateCfg()
+        cfg.actor, cfg.critic = nets.actor.desc, nets.critic.desc
+        cfg.head = policy.head
+        cfg.act_dim = policy.action_dim
+        cfg.use_huber = int(bool(policy.use_huber_loss))
+        cfg.normalize_adv = int(self.normalize_adv)
+        cfg.normalize_values = int(self.normalize_values)
+        cfg.vf_clip_enabled = int(policy.vf_clip is not None)
+        cfg.min_std = policy.min_std
+        self.cfg = cfg
+        dev = self.device
+        self.hparams_host = torch.zeros(HP["COUNT"], dtype=torch.float64, pin_memory=True)
+        self.hparams = torch.zeros(HP["COUNT"], dtype=torch.float64, device=dev)
+        self.epoch_stats = torch.zeros(ST["COUNT"], dtype=torch.float64, device=dev)
+        self.epoch_stats_host = torch.zeros(ST["COUNT"], dtype=torch.float64, pin_memory=True)
+        self.mb_cursor = torch.zeros(1, dtype=torch.int32, device=dev)
+        ws_bytes = load().ppoaf_update_workspace_bytes(C.byref(cfg), self.batch_size)
+        self.workspace = torch.zeros(ws_bytes + 256, dtype=torch.uint8, device=dev)
+        self.null_state = torch.tensor([0.0, 1.0, 1e-4], dtype=torch.float64, device=dev)
+        self._graphs = {}
+        self._graph_key = None
+        self._perm_dev = None
+        self.launches_per_step = None
+
+    # -- hyper-parameters (read by the kernels every step) -----------------------------
+    def refresh_hparams(self):
+        p, h = self.policy, self.hparams_host
+        h[HP["LR"]] = float(p.lr())
+        h[HP["ENTROPY_WEIGHT"]] = float(p.entropy_weight())
+        h[HP["SURR_CLIP"]] = float(p.surr_clip)
+        h[HP["GRAD_CLIP"]] = -1.0 if p.gradient_clip is None else float(p.gradient_clip)
+        h[HP["KL_WEIGHT"]] = float(p.kl_loss_weight)
+        h[HP["VF_CLIP"]] = -1.0 if p.vf_clip is None else float(p.vf_clip)
+        h[HP["BETA1"]], h[HP["BETA2"]], h[HP["ADAM_EPS"]] = 0.9, 0.999, 1e-5
+        h[HP["INV_WORLD"]] = 1.0 / mpi_utils.get_num_procs()
+        self.hparams.copy_(h, non_blocking=True)
+
+    # -- buffers struct for a given dataset / minibatch size ---------------------------------------------
+    def _bufs(self, ds, rows):
+        nets = self.policy.nets
+        b = _lib.UpdateBufs()
+        b.critic_obs, b.obs = ds.critic_observations.data_ptr(), ds.observations.data_ptr()
+        b.raw_actions = ds.raw_actions.data_ptr()
+        b.advantages, b.log_probs = ds.advantages.data_ptr(), ds.log_probs.data_ptr()
+        b.rewards_to_go, b.values = ds.rewards_to_go.data_ptr(), ds.values.data_ptr()
+        b.perm = self._perm_dev.data_ptr()
+        b.mb_adv_stats, b.mb_val_stats = self._mb_adv_stats.data_ptr(), self._mb_val_stats.data_ptr()
+        b.params, b.grads = nets.flat_params.data_ptr(), nets.flat_grads.data_ptr()
+        b.adam_m, b.adam_v, b.adam_step = nets.adam_m.data_ptr(), nets.adam_v.data_ptr(), nets.adam_step.data_ptr()
+        b.hparams, b.epoch_stats = self.hparams.data_ptr(), self.epoch_stats.data_ptr()
+        b.mb_cursor = self.mb_cursor.data_ptr()
+        ws = self.workspace.data_ptr()
+        b.workspace = (ws + 255) // 256 * 256
+        b.workspace_bytes = self.workspace.numel() - 256
+        b.n_flat = len(ds)
+        b.batch, b.batch_size = int(rows), self.batch_size
+        return b
+
+    def _step_eager(self, bufs):
+        lib, cfg = load(), self.cfg
+        check(lib.ppoaf_ppo_minibatch_grads(C.byref(cfg), C.byref(bufs), stream_ptr()), "ppoaf_ppo_minibatch_grads")
+        if bufs.batch > 1:
+            mpi_utils.mpi_avg_gradients(self.policy.nets.flat_grads)
+        check(lib.ppoaf_ppo_minibatch_apply(C.byref(cfg), C.byref(bufs), stream_ptr()), "ppoaf_ppo_minibatch_apply")
+
+    def _ensure_epoch_buffers(self, n):
+        n_mb = (n + self.batch_size - 1) // self.batch_size
+        dev = self.device
+        if self._perm_dev is None or self._perm_dev.numel() != n:
+            self._perm_dev = torch.empty(n, dtype=torch.int64, device=dev)
+            self._perm_host = torch.empty(n, dtype=torch.int64, pin_memory=True)
+            self._mb_adv_stats = torch.zeros((n_mb, 2), dtype=torch.float32, device=dev)
+            self._mb_val_stats = torch.zeros((n_mb, 2), dtype=torch.float32, device=dev)
+            self._mb_val_triples = torch.zeros((n_mb, 3), dtype=torch.float64, device=dev)
+            self._graphs.clear()
+        return n_mb
+
+    def _launch_step(self, ds, rows):
+        key = (rows, ds.observations.data_ptr(), ds.critic_observations.data_ptr(), ds.values.data_ptr(),
+               ds.advantages.data_ptr())
+        if not self.use_graphs or rows < 2:
+            self._step_eager(self._bufs(ds, rows))
+            return
+        g = self._graphs.get(key)
+        if g is None:
+            if len(self._graphs) > 8:
+                self._graphs.clear()
+            bufs = self._bufs(ds, rows)
+            graph = torch.cuda.CUDAGraph()
+            torch.cuda.synchronize(self.device)
+            with torch.cuda.graph(graph):
+                self._step_eager(bufs)
+            g = (graph, bufs)
+            self._graphs[key] = g
+        g[0].replay()
+
+    # -- one epoch = PPO._ppo_batch_train -------------------------------------------------------------------
+    def run_epoch(self, ds):
+        n = len(ds)
+        n_mb = self._ensure_epoch_buffers(n)
+        lib = load()
+        self.refresh_hparams()
+        perm = draw_minibatch_permutation(n)
+        self._perm_host.copy_(perm)
+        self._perm_dev.copy_(self._perm_host, non_blocking=True)
+        check(lib.ppoaf_epoch_prepare(ptr(self._perm_dev), ptr(ds.advantages), ptr(ds.rewards_to_go), n, self.batch_size,
+                                      ptr(self._mb_adv_stats), ptr(self._mb_val_triples), stream_ptr()),
+              "ppoaf_epoch_prepare")
+        if self.normalize_values:
+            triples = mpi_utils.all_gather_cat(self._mb_val_triples).contiguous()     # [R, n_mb, 3]
+            state = self.value_normalizer.running_stats.state if self.value_normalizer is not None else self.null_state
+            check(lib.ppoaf_value_stats_sequence(ptr(state), ptr(triples), triples.shape[0], n_mb, 1e-8,
+                                                 ptr(self._mb_val_stats), stream_ptr()), "ppoaf_value_stats_sequence")
+        self.epoch_stats.zero_()
+        self.mb_cursor.zero_()
+        for k in range(n_mb):
+            rows = min(self.batch_size, n - k * self.batch_size)
+            self._launch_step(ds, rows)
+        self.epoch_stats_host.copy_(self.epoch_stats, non_blocking=True)
+        torch.cuda.current_stream(self.device).synchronize()            # the one host sync of the epoch
+        return self.epoch_stats_host.clone()
+
+
+def _get_engine(ppo, policy_id, batch_size):
+    policy = ppo.policies[policy_id]
+    eng = getattr(policy, "_engine", None)
+    vn = ppo.value_normalizers[policy_id] if getattr(ppo, "normalize_values", False) else None
+    if (eng is None or eng.batch_size != batch_size or eng.normalize_adv != bool(ppo.normalize_adv)
+            or eng.normalize_values != bool(ppo.normalize_values) or eng.value_normalizer is not vn):
+        eng = UpdateEngine(policy, batch_size, ppo.normalize_adv, ppo.normalize_values, vn)
+        policy._engine = eng
+    return eng
+
+
+def ppo_batch_train(ppo, data_loader, policy_id):
+    """
+    Drop-in for `PPO._ppo_batch_train(self, data_loader, policy_id)` (ppo.py:2274-2485).
+    `data_loader` needs `.dataset` (a built ppo_and_friends_b200 PPODataset) and `.batch_size`.
+    """
+    policy = ppo.policies[policy_id]
+    if policy.frozen:
+        return
+    ds = data_loader.dataset
+    eng = _get_engine(ppo, policy_id, int(data_loader.batch_size))
+    st = eng.run_epoch(ds).numpy()
+    if st[ST["BAD_VALUE"]] > 0:
+        mpi_utils.abort("ERROR: evaluate value or action prediction contains nan values!")
+    if st[ST["BAD_RATIO"]] > 0:
+        mpi_utils.abort("ERROR: ratios are nan or inf!")
+    sums = np.array([st[ST["COUNTER"]], st[ST["ENTROPY"]], st[ST["ACTOR_LOSS"]], st[ST["CRITIC_LOSS"]], st[ST["KL"]]])
+    if mpi_utils.get_num_procs() > 1:                                   # ppo.py:2471-2475, one packed all-reduce
+        t = torch.as_tensor(sums).to(policy.device)
+        mpi_utils.allreduce_sum_(t)
+        sums = t.cpu().numpy()
+    counter, total_entropy, total_actor, total_critic, total_kl = sums
+    w_entropy = total_entropy * policy.entropy_weight()
+    sd = ppo.status_dict[policy_id]
+    sd["weighted entropy"] = w_entropy / counter
+    sd["actor loss"] = total_actor / counter
+    sd["critic loss"] = total_critic / counter
+    sd["kl avg"] = total_kl / counter
+
+
+class _Loader:
+    """What the trainer needs from a DataLoader: `.dataset` and `.batch_size`."""
+
+    def __init__(self, dataset, batch_size):
+        self.dataset, self.batch_size = dataset, batch_size
+
+
+def train_policies(ppo):
+    """
+    The update half of one `PPO.learn` iteration (ppo.py:2178-2238): per policy, up to
+    `epochs_per_iter` epochs with optional advantage recalculation and KL early stop, then
+    `clear_dataset` is left to the caller exactly where the reference does it.
+    Returns {policy_id: epochs actually run}.
+    """
+    epochs_run = {}
+    for policy_id, policy in ppo.policies.items():
+        if policy.frozen:
+            continue
+        loader = _Loader(policy.dataset, ppo.batch_size)
+        n_ep = 0
+        for epoch_idx in range(ppo.epochs_per_iter):
+            if epoch_idx > 0 and getattr(ppo, "recalc_advantages", False):
+                loader.dataset.recalculate_advantages()
+            ppo_batch_train(ppo, loader, policy_id)
+            n_ep += 1
+            if ppo.status_dict[policy_id]["kl avg"] > policy.target_kl:
+                if getattr(ppo, "verbose", False):
+                    mpi_utils.rank_print("Target KL of {} has been reached. Ending early (after {} epochs)".format(
+                        policy.target_kl, epoch_idx + 1))
+                break
+        epochs_run[policy_id] = n_ep
+    return epochs_run
+
+
+class PPOUpdateState:
+    """
+    The slice of the reference `PPO` object the update path reads (ppo.py:126-708): policies, batch
+    size, epochs, normalisation switches, value normalisers and the status dict.  A real reference
+    `PPO` instance can be passed to `ppo_batch_train` / `train_policies` instead (duck-typed).
+    """
+
+    def __init__(self, policies, batch_size=256, epochs_per_iter=10, normalize_adv=True, normalize_values=True,
+                 recalc_advantages=False, device="cuda", verbose=False):
+        self.policies = OrderedDict(policies)
+        self.batch_size, self.epochs_per_iter = batch_size, epochs_per_iter
+        self.normalize_adv, self.normalize_values = normalize_adv, normalize_values
+        self.recalc_advantages = recalc_advantages
+        self.verbose = verbose
+        self.device = torch.device(device)
+        self.status_dict = OrderedDict({"global status": OrderedDict(iteration=0, timesteps=0)})
+        self.value_normalizers = {}
+        for pid in self.policies:
+            self.status_dict[pid] = OrderedDict()
+            if normalize_values:
+                self.value_normalizers[pid] = RunningStatNormalizer(pid + "-value_normalizer", self.device)

@@ -1,0 +1,384 @@
+"""
+GPU parity tests proper (run with -m gpu on the B200): every comparison goes through the C ABI of
+libppoaf_b200.so and checks the CUDA result against the CPU oracle (oracle/) or directly against
+the golden fixtures recorded from the unmodified reference (tests/golden/*.npz).
+
+Tolerances (BASELINE.json north_star): integer outputs bit-exact; advantages / returns within
+1e-5 relative (measured against max(|ref|, 1) because advantages cross zero); losses and post-epoch
+parameters within 1e-4 relative (parameters: |err| <= 1e-4*|ref| + 1e-6, since biases start at 0).
+"""
+import numpy as np
+import pytest
+import torch
+
+from conftest import load_golden, rollout_from_golden
+from helpers import make_policy, policy_kwargs_from_golden, rel_err, run_device_rollout
+
+pytestmark = pytest.mark.gpu
+
+SEG_CASES = ["seg_single", "seg_multi", "seg_bsclip", "seg_nogae", "seg_dynclip", "seg_noclip", "seg_long"]
+
+
+def dev(x, dtype=None):
+    t = torch.as_tensor(np.ascontiguousarray(x))
+    if dtype is not None:
+        t = t.to(dtype)
+    return t.cuda().contiguous()
+
+
+# ----------------------------------------------------------------------------------------- A2..A6
+@pytest.mark.parametrize("name", SEG_CASES)
+@pytest.mark.parametrize("tensor_bootstrap", [False, True])
+def test_rollout_to_dataset_matches_reference(name, tensor_bootstrap):
+    g = load_golden(name)
+    ro = rollout_from_golden(g)
+    pol = make_policy(ro, **policy_kwargs_from_golden(g))
+    ds = run_device_rollout(pol, ro, tensor_bootstrap)
+    # integer outputs: bit-exact
+    assert np.array_equal(ds.ep_lens, g["ep_lens"])
+    assert np.array_equal(ds.seg_terminal, g["seg_terminal"])
+    flag = ds.seg_flag.cpu().numpy()
+    ends = np.cumsum(g["ep_lens"]) - 1
+    expect = np.zeros(len(flag), dtype=np.uint8)
+    expect[ends] = 1 + 2 * g["seg_terminal"].astype(np.uint8)
+    assert np.array_equal(flag, expect)
+    # gathered fields: bit-exact (pure data movement)
+    for k in ("observations", "next_observations", "critic_observations", "actions", "raw_actions", "values",
+              "log_probs"):
+        got = getattr(ds, k).cpu().numpy()
+        assert got.dtype == g[k].dtype and got.shape == g[k].shape, k
+        assert np.array_equal(got, g[k]), k
+    # floats: 1e-5 relative against the float64 reference values
+    adv, rtg = ds.advantages.cpu().numpy(), ds.rewards_to_go.cpu().numpy()
+    assert rel_err(adv, g["advantages_f64"], 1.0) < 1e-5
+    assert rel_err(rtg, g["rewards_to_go_asrun"], 1.0) < 1e-5
+    assert len(ds) == len(g["advantages"])
+
+
+def random_segments(rng, n, max_len):
+    lens = []
+    left = n
+    while left > 0:
+        L = int(min(left, rng.integers(1, max_len + 1)))
+        lens.append(L)
+        left -= L
+    return np.array(lens, dtype=np.int64)
+
+
+@pytest.mark.parametrize("n,max_len,use_gae", [(1, 1, True), (7, 3, True), (2048, 40, True), (2049, 64, False),
+                                              (50_001, 300, True), (30_000, 30_000, True), (9_000, 5_000, False),
+                                              (262_144, 64, True)])
+def test_segscan_vs_oracle(n, max_len, use_gae):
+    from oracle.segments import flat_segscan_reference
+    from ppo_and_friends_b200 import ops
+    rng = np.random.default_rng(n + max_len)
+    lens = random_segments(rng, n, max_len)
+    n_seg = len(lens)
+    rewards = rng.standard_normal(n).astype(np.float32)
+    values = rng.standard_normal(n).astype(np.float32)
+    terminal = rng.random(n_seg) < 0.5
+    v_boot = np.where(terminal, 0.0, rng.standard_normal(n_seg) * 3).astype(np.float32)
+    r_boot = np.clip(v_boot, -2.0, 2.0).astype(np.float32)
+    off = np.zeros(n_seg + 1, dtype=np.int64)
+    np.cumsum(lens, out=off[1:])
+    flag = np.zeros(n, dtype=np.uint8)
+    flag[off[1:] - 1] = 1 + 2 * terminal.astype(np.uint8)
+    adv, rtg = ops.gae_rtg_segscan(dev(rewards), dev(values), dev(flag), dev(off), dev(v_boot), dev(r_boot),
+                                   0.99, 0.95, use_gae)
+    ref_adv, ref_rtg = flat_segscan_reference(rewards, values, lens, v_boot, r_boot, 0.99, 0.95, use_gae)
+    assert rel_err(adv.cpu().numpy(), ref_adv, 1.0) < 1e-5
+    assert rel_err(rtg.cpu().numpy(), ref_rtg, 1.0) < 1e-5
+    # fp64 accumulation makes the fp32 results equal to the rounded reference almost everywhere
+    assert np.mean(adv.cpu().numpy() == ref_adv.astype(np.float32)) > 0.999
+
+
+def test_segscan_full_size_properties():
+    """BASELINE config 2 size (2^22 timesteps): size-independent properties instead of the slow oracle."""
+    from ppo_and_friends_b200 import ops
+    n = 1 << 22
+    rng = np.random.default_rng(5)
+    lens = random_segments(rng, n, 64)
+    n_seg = len(lens)
+    off = np.zeros(n_seg + 1, dtype=np.int64)
+    np.cumsum(lens, out=off[1:])
+    flag = np.zeros(n, dtype=np.uint8)
+    flag[off[1:] - 1] = 1
+    r = torch.randn(n, device="cuda")
+    v = torch.randn(n, device="cuda")
+    vb = torch.randn(n_seg, device="cuda")
+    rb = vb.clamp(-100, 100)
+    args = (dev(flag), dev(off))
+    adv, rtg = ops.gae_rtg_segscan(r, v, *args, vb, rb, 0.99, 0.95, True)
+    # (1) linearity: scaling every input by 2 (a power of two: exact in fp) scales every output by 2
+    adv2, rtg2 = ops.gae_rtg_segscan(2 * r, 2 * v, *args, 2 * vb, 2 * rb, 0.99, 0.95, True)
+    assert torch.equal(adv2, 2 * adv) and torch.equal(rtg2, 2 * rtg)
+    # (2) the recurrence itself, checked element-wise in fp64 on device: RTG_t = r_t + g*RTG_{t+1} inside a
+    #     segment and r_t + g*r_boot at its end; A_t = delta_t + g*l*A_{t+1}
+    flag_d = dev(flag).bool()
+    seg_id = torch.cumsum(flag_d.long(), 0) - flag_d.long()
+    nxt_rtg = torch.where(flag_d, rb[seg_id].double(), torch.roll(rtg, -1).double())
+    assert torch.max(torch.abs(rtg.double() - (r.double() + 0.99 * nxt_rtg)) / nxt_rtg.abs().clamp(min=1)) < 1e-6
+    nxt_v = torch.where(flag_d, vb[seg_id], torch.roll(v, -1))
+    nxt_a = torch.where(flag_d, torch.zeros((), device="cuda", dtype=torch.float64), torch.roll(adv, -1).double())
+    delta = r.double() + (torch.tensor(0.99, dtype=torch.float32, device="cuda") * nxt_v).double() - v.double()
+    assert torch.max(torch.abs(adv.double() - (delta + 0.99 * 0.95 * nxt_a)) / nxt_a.abs().clamp(min=1)) < 1e-6
+    # (3) determinism / idempotence: a second launch reproduces the first bit-for-bit
+    adv3, rtg3 = ops.gae_rtg_segscan(r, v, *args, vb, rb, 0.99, 0.95, True)
+    assert torch.equal(adv3, adv) and torch.equal(rtg3, rtg)
+
+
+def test_recalculate_advantages_matches_oracle():
+    from oracle.segments import flat_segscan_reference
+    g = load_golden("seg_single")
+    ro = rollout_from_golden(g)
+    pol = make_policy(ro, **policy_kwargs_from_golden(g))
+    ds = run_device_rollout(pol, ro)
+    new_vals = np.random.default_rng(1).standard_normal(len(ds)).astype(np.float32)
+    ds.values.copy_(torch.as_tensor(new_vals))
+    rtg_before = ds.rewards_to_go.clone()
+    ds.recalculate_advantages()
+    ref_adv, _ = flat_segscan_reference(ds.rewards.cpu().numpy(), new_vals, g["ep_lens"], ds.v_boot.cpu().numpy(),
+                                        ds.r_boot.cpu().numpy(), 0.99, 0.95, True)
+    assert rel_err(ds.advantages.cpu().numpy(), ref_adv, 1.0) < 1e-5
+    assert torch.equal(ds.rewards_to_go, rtg_before)
+
+
+# ----------------------------------------------------------------------------------------- N1..N4
+@pytest.mark.parametrize("n,dim", [(1, 1), (50, 1), (4097, 1), (64, 5), (1000, 5), (7, 376), (5000, 376), (333, 18),
+                                   (2048, 54), (100, 1030)])
+def test_batch_moments_and_merge_vs_oracle(n, dim):
+    from oracle.stats import OracleRunningMeanStd
+    from ppo_and_friends_b200.utils.stats import RunningMeanStd
+    rng = np.random.default_rng(n * 31 + dim)
+    mu = rng.uniform(-3, 3, dim)
+    sd = rng.uniform(0.1, 10, dim)
+    rms = RunningMeanStd(shape=(dim,))
+    ref = OracleRunningMeanStd(shape=(dim,))
+    for rep in range(3):
+        x = (rng.standard_normal((n, dim)) * sd + mu).astype(np.float32)
+        rms.update(x)
+        ref.update(x.astype(np.float64))
+        scale = np.sqrt(np.asarray(ref.variance, dtype=np.float64)) + np.abs(ref.mean)
+        assert np.max(np.abs(rms.mean - ref.mean) / scale) < 1e-5
+        assert rel_err(rms.variance, ref.variance, 1e-12) < 1e-5
+        assert abs(rms.count - ref.count) < 1e-9 * ref.count
+
+
+def test_stats_match_reference_golden():
+    from ppo_and_friends_b200.utils.misc import RunningStatNormalizer
+    from ppo_and_friends_b200.utils.stats import RunningMeanStd
+    g = load_golden("stats")
+    rms = RunningMeanStd(shape=(5,))
+    for i in range(3):
+        rms.update(g[f"vec64_batch{i}"])
+        np.testing.assert_allclose(rms.mean, g[f"vec64_mean{i}"], rtol=1e-5, atol=1e-6)
+        np.testing.assert_allclose(rms.variance, g[f"vec64_var{i}"], rtol=1e-5)
+        assert abs(rms.count - float(g[f"vec64_count{i}"])) < 1e-9
+    norm = RunningStatNormalizer("vn", "cuda")
+    for i in range(4):
+        y = norm.normalize(torch.as_tensor(g[f"sc_in{i}"]).cuda())
+        np.testing.assert_allclose(y.cpu().numpy(), g[f"sc_out{i}"], rtol=1e-5, atol=1e-6)
+        np.testing.assert_allclose(norm.running_stats.mean, g[f"sc_mean{i}"], rtol=1e-5, atol=1e-7)
+        np.testing.assert_allclose(norm.running_stats.variance, g[f"sc_var{i}"], rtol=1e-5)
+    np.testing.assert_allclose(norm.denormalize(g["sc_denorm_in"]).cpu().numpy(), g["sc_denorm_out"], rtol=1e-6, atol=1e-6)
+    np.testing.assert_allclose(norm.normalize(g["sc_denorm_in"], update_stats=False).cpu().numpy(),
+                               g["sc_noupdate_out"], rtol=1e-5, atol=1e-6)
+
+
+@pytest.mark.parametrize("n,dim", [(1000, 376), (77, 5), (4099, 1), (64, 18)])
+def test_normalize_clip_vs_oracle(n, dim):
+    from oracle.stats import OracleRunningMeanStd, normalize_clip_obs
+    from ppo_and_friends_b200 import ops
+    from ppo_and_friends_b200.utils.stats import RunningMeanStd
+    rng = np.random.default_rng(dim)
+    x = (rng.standard_normal((n, dim)) * rng.uniform(0.1, 10, dim) + rng.uniform(-3, 3, dim)).astype(np.float32)
+    x[0, 0] = 1e4                                                      # something for the clip to bite
+    rms = RunningMeanStd(shape=(dim,))
+    rms.update(x)
+    y = ops.normalize_clip(dev(x), rms.state, dim, 1e-8, -10.0, 10.0).cpu().numpy()
+    ref = normalize_clip_obs(x, rms.mean, rms.variance)
+    np.testing.assert_allclose(y, ref, rtol=2e-6, atol=2e-6)
+    # idempotence property: statistics of normalised data are (0, 1)
+    if n >= 1000:
+        x2 = rng.standard_normal((n, dim)).astype(np.float32) * 3 + 1
+        r2 = RunningMeanStd(shape=(dim,), epsilon=1e-12)
+        r2.update(x2)
+        y2 = ops.normalize_clip(dev(x2), r2.state, dim, 0.0)
+        r3 = RunningMeanStd(shape=(dim,), epsilon=1e-12)
+        r3.update(y2)
+        assert np.max(np.abs(r3.mean)) < 1e-5 and np.max(np.abs(r3.variance - 1)) < 1e-4
+
+
+# ----------------------------------------------------------------------------------------- P1/P2
+@pytest.mark.parametrize("dims,act,rows", [([8, 64, 64, 64, 2], "leaky_relu", 512), ([376, 256, 256, 256, 17], "tanh", 512),
+                                           ([18, 128, 128, 128, 5], "leaky_relu", 128), ([54, 256, 256, 256, 1], "relu", 130),
+                                           ([4, 128, 128, 128, 2], "leaky_relu", 3), ([5, 3], "tanh", 9)])
+def test_mlp_forward_vs_torch_fp32(dims, act, rows):
+    from oracle.update import ACTIVATIONS
+    from ppo_and_friends_b200 import _lib, ops
+    torch.manual_seed(sum(dims))
+    desc = _lib.MlpDesc.make(dims, act)
+    offs, total = _lib.param_layout(desc)
+    flat = torch.zeros(total)
+    Ws = []
+    for l in range(len(dims) - 1):
+        W = torch.randn(dims[l + 1], dims[l]) / np.sqrt(dims[l])
+        b = torch.randn(dims[l + 1]) * 0.1
+        flat[offs[2 * l]:offs[2 * l] + W.numel()] = W.reshape(-1)
+        flat[offs[2 * l + 1]:offs[2 * l + 1] + b.numel()] = b
+        Ws.append((W, b))
+    x = torch.randn(rows * 2, dims[0])
+    idx = torch.randperm(rows * 2)[:rows]
+    y = ops.mlp_forward(desc, flat.cuda(), x.cuda(), idx=idx.cuda()).cpu()
+    h = x[idx].double()
+    for l, (W, b) in enumerate(Ws):
+        h = h @ W.double().t() + b.double()
+        if l + 1 < len(Ws):
+            h = ACTIVATIONS[act](h)
+    np.testing.assert_allclose(y.numpy(), h.numpy(), rtol=2e-5, atol=2e-5)
+
+
+@pytest.mark.parametrize("discrete", [False, True])
+def test_head_evaluate_vs_oracle(discrete):
+    from oracle.update import categorical_from_probs, gaussian_std, gaussian_tanh_log_prob
+    from ppo_and_friends_b200 import _lib, ops
+    torch.manual_seed(3)
+    n = 300
+    if discrete:
+        logits = torch.randn(n, 5) * 3
+        acts = torch.randint(0, 5, (n, 1))
+        p, lg = categorical_from_probs(torch.softmax(logits, -1))
+        ref_lp = lg.gather(-1, acts).reshape(-1)
+        ref_ent = -(p * lg).sum(-1)
+        lp, ent = ops.head_evaluate(_lib.HEAD_CATEGORICAL, logits.cuda(), None, acts.cuda())
+    else:
+        mu = torch.randn(n, 17)
+        log_std = torch.randn(17)
+        log_std[0] = -9.0                                                # below min_std
+        x = mu + torch.randn(n, 17) * 2
+        x[0, 0] = 12.0                                                   # saturates tanh -> the 1e-6 clamp
+        sd = gaussian_std(log_std)
+        ref_lp = gaussian_tanh_log_prob(mu, sd, x)
+        ref_ent = -gaussian_tanh_log_prob(mu, sd, mu)
+        lp, ent = ops.head_evaluate(_lib.HEAD_GAUSSIAN_TANH, mu.cuda(), log_std.cuda(), x.cuda())
+    np.testing.assert_allclose(lp.cpu().numpy(), ref_lp.numpy(), rtol=1e-5, atol=1e-5)
+    np.testing.assert_allclose(ent.cpu().numpy(), ref_ent.numpy(), rtol=1e-5, atol=1e-5)
+
+
+# ----------------------------------------------------------------------------------------- P4
+def test_clip_adam_vs_oracle_restated_torch():
+    from ppo_and_friends_b200 import ops
+    from ppo_and_friends_b200._lib import HP
+    torch.manual_seed(9)
+    n_a, n_c = 1024, 516
+    p = torch.randn(n_a + n_c)
+    m = torch.zeros_like(p); v = torch.zeros_like(p)
+    pd, md, vd = p.cuda(), m.cuda(), v.cuda()
+    step = torch.zeros(1, dtype=torch.int64, device="cuda")
+    hp = torch.zeros(HP["COUNT"], dtype=torch.float64)
+    hp[HP["LR"]], hp[HP["GRAD_CLIP"]], hp[HP["BETA1"]], hp[HP["BETA2"]], hp[HP["ADAM_EPS"]], hp[HP["INV_WORLD"]] = \
+        3e-4, 0.5, 0.9, 0.999, 1e-5, 1.0
+    hpd = hp.cuda()
+    pa, pc = p[:n_a].clone().requires_grad_(True), p[n_a:].clone().requires_grad_(True)
+    oa = torch.optim.Adam([pa], lr=3e-4, eps=1e-5)
+    oc = torch.optim.Adam([pc], lr=3e-4, eps=1e-5)
+    for t in range(5):
+        g = torch.randn(n_a + n_c) * (3.0 if t % 2 == 0 else 0.01)      # clipped and unclipped steps
+        ops.clip_adam_step(pd, g.cuda(), md, vd, step, hpd, n_a, n_c)
+        pa.grad, pc.grad = g[:n_a].clone(), g[n_a:].clone()
+        torch.nn.utils.clip_grad_norm_([pa], 0.5); oa.step()
+        torch.nn.utils.clip_grad_norm_([pc], 0.5); oc.step()
+        ref = torch.cat([pa.detach(), pc.detach()])
+        np.testing.assert_allclose(pd.cpu().numpy(), ref.numpy(), rtol=2e-6, atol=1e-7)
+    assert int(step.item()) == 5
+
+
+# ----------------------------------------------------------------------------------------- P1..P6 end to end
+UPD_CASES = ["upd_gauss", "upd_cat", "upd_opts", "upd_skip1", "upd_nonorm"]
+
+
+def policy_from_update_golden(g):
+    nan = lambda v: None if np.isnan(v) else float(v)
+    ro = rollout_from_golden(g)
+    pol = make_policy(ro, act=str(g["hp_activation"]), actor_hidden=int(g["hp_actor_hidden"]),
+                      critic_hidden=int(g["hp_critic_hidden"]), depth=int(g["hp_depth"]),
+                      dist_range=float(g["hp_dist_range"]), lr=float(g["hp_lr"]),
+                      entropy_weight=float(g["hp_entropy_weight"]), surr_clip=float(g["hp_surr_clip"]),
+                      vf_clip=nan(g["hp_vf_clip"]), gradient_clip=nan(g["hp_gradient_clip"]),
+                      kl_loss_weight=float(g["hp_kl_loss_weight"]), use_huber_loss=bool(g["hp_use_huber_loss"]),
+                      gamma=float(g["hp_gamma"]), lambd=float(g["hp_lambd"]))
+    pol.actor.load_state_dict({k[len("init/actor/param/"):]: g[k] for k in g if k.startswith("init/actor/param/")})
+    pol.critic.load_state_dict({k[len("init/critic/param/"):]: g[k] for k in g if k.startswith("init/critic/param/")})
+    return ro, pol
+
+
+@pytest.mark.parametrize("name", UPD_CASES)
+@pytest.mark.parametrize("use_graphs", [True, False])
+def test_update_matches_reference(name, use_graphs, monkeypatch):
+    from ppo_and_friends_b200.ppo import PPOUpdateState, _Loader, ppo_batch_train
+    monkeypatch.setenv("PPOAF_NO_GRAPH", "0" if use_graphs else "1")
+    g = load_golden(name)
+    ro, pol = policy_from_update_golden(g)
+    ds = run_device_rollout(pol, ro)
+    np.testing.assert_allclose(ds.advantages.cpu().numpy(), g["ds_advantages"], rtol=1e-5, atol=1e-5)
+    state = PPOUpdateState({"pol": pol}, batch_size=int(g["hp_B"]), epochs_per_iter=int(g["hp_epochs"]),
+                           normalize_adv=bool(g["hp_normalize_adv"]), normalize_values=bool(g["hp_normalize_values"]))
+    torch.manual_seed(int(g["hp_perm_seed"]))
+    loader = _Loader(ds, int(g["hp_B"]))
+    for ep in range(int(g["hp_epochs"])):
+        ppo_batch_train(state, loader, "pol")
+        # minibatch permutation gathers: bit-exact
+        assert np.array_equal(pol._engine._perm_dev.cpu().numpy(), g[f"ep{ep}/batch_idxs"])
+        sd = state.status_dict["pol"]
+        got = np.array([sd["actor loss"], sd["critic loss"], sd["kl avg"], sd["weighted entropy"]])
+        ref = g[f"ep{ep}/status"]
+        # losses: 1e-4 relative (actor loss / kl are means of O(1) terms that cancel: floor at 1e-3)
+        assert rel_err(got, ref, 1e-3) < 1e-4, (got, ref)
+        for net, obj in (("actor", pol.actor), ("critic", pol.critic)):
+            for k, v in obj.state_dict().items():
+                np.testing.assert_allclose(v.cpu().numpy(), g[f"ep{ep}/{net}/param/{k}"], rtol=1e-4, atol=1e-6,
+                                           err_msg=f"{net}/{k} epoch {ep}")
+        if bool(g["hp_normalize_values"]):
+            rs = state.value_normalizers["pol"].running_stats
+            np.testing.assert_allclose([float(rs.mean), float(rs.variance), rs.count], g[f"ep{ep}/vn"], rtol=1e-5)
+        np.testing.assert_allclose(ds.values.cpu().numpy(), g[f"ep{ep}/dataset_values"], rtol=1e-4, atol=1e-5)
+
+
+def test_update_vs_oracle_humanoid_shape():
+    """BASELINE config 4 network shapes (376-256^3-17 / 376-256^3-1, Tanh, B=512) against the torch-CPU oracle."""
+    from oracle.update import OracleUpdater
+    from ppo_and_friends_b200.ppo import PPOUpdateState, _Loader, ppo_batch_train
+    from ppo_and_friends_b200.synthetic import make_rollout
+    ro = make_rollout(seed=77, T=32, E=64, obs_dim=376, act_dim=17, max_ts_per_ep=16, obs_scale=False)
+    torch.manual_seed(5)
+    pol = make_policy(ro, act="tanh", actor_hidden=256, critic_hidden=256, dist_range=0.4, lr=1e-4)
+    # old log-probs consistent with the initial actor so ratios start near 1
+    with torch.no_grad():
+        for a in ro.agents:
+            obs = ro.obs[a].reshape(-1, 376)
+            mu = pol.actor(obs).cpu().numpy()
+            sd = np.maximum(np.log1p(np.exp(-0.5)), 0.01)
+            raw = (mu + sd * np.random.default_rng(1).standard_normal(mu.shape)).astype(np.float32)
+            ro.raw_actions[a] = raw.reshape(ro.T, ro.E, 17)
+            _, lp, _ = pol.evaluate(ro.critic_obs[a].reshape(-1, 376), obs, raw)
+            ro.log_probs[a] = lp.cpu().numpy().reshape(ro.T, ro.E)
+            ro.values[a] = pol.critic(ro.critic_obs[a].reshape(-1, 376)).cpu().numpy().reshape(ro.T, ro.E)
+    ds = run_device_rollout(pol, ro)
+    host = {k: getattr(ds, k).cpu().numpy().copy() for k in ("critic_observations", "observations", "raw_actions",
+                                                               "advantages", "log_probs", "rewards_to_go", "values")}
+    oracle = OracleUpdater({k: v.cpu().numpy() for k, v in pol.actor.state_dict().items()},
+                           {k: v.cpu().numpy() for k, v in pol.critic.state_dict().items()}, "tanh", False, lr=1e-4)
+    state = PPOUpdateState({"pol": pol}, batch_size=512, epochs_per_iter=1)
+    torch.manual_seed(11)
+    ppo_batch_train(state, _Loader(ds, 512), "pol")
+    perm = pol._engine._perm_dev.cpu().numpy()
+    st = oracle.batch_train([host], [perm], 512)
+    sd = state.status_dict["pol"]
+    got = np.array([sd["actor loss"], sd["critic loss"], sd["kl avg"], sd["weighted entropy"]])
+    ref = np.array([st["actor loss"], st["critic loss"], st["kl avg"], st["weighted entropy"]])
+    assert rel_err(got, ref, 1e-3) < 1e-4, (got, ref)
+    ref_state = oracle.state()
+    for net, obj in (("actor", pol.actor), ("critic", pol.critic)):
+        for k, v in obj.state_dict().items():
+            np.testing.assert_allclose(v.cpu().numpy(), ref_state[f"{net}/param/{k}"], rtol=1e-4, atol=1e-6, err_msg=k)
+    np.testing.assert_allclose(ds.values.cpu().numpy(), host["values"], rtol=1e-4, atol=1e-5)

@@ -1,0 +1,209 @@
+"""
+CPU tests (-m "not gpu"): the C-ABI library loads and exports every symbol include/ppoaf_b200.h
+declares, the host-side logic (permutation protocol, parameter layout, ring layout, communicator
+layer on gloo with world_size 2) behaves, and the product path refuses to run without CUDA.
+No compute entry point is called here.
+"""
+import os
+import re
+import subprocess
+import sys
+
+import numpy as np
+import pytest
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_library_exports_every_declared_symbol():
+    from ppo_and_friends_b200 import _lib
+    from ppo_and_friends_b200.build import build
+    build()
+    header = open(os.path.join(ROOT, "include", "ppoaf_b200.h")).read()
+    declared = set(re.findall(r"\b(ppoaf_[a-z_0-9]+)\s*\(", header))
+    assert declared, "no declarations parsed"
+    lib = _lib.load()
+    for name in declared:
+        assert hasattr(lib, name), f"{name} declared in the header but not exported"
+    assert set(_lib.EXPORTED_SYMBOLS) == declared
+    assert lib.ppoaf_abi_version() == 1
+
+
+def test_sizing_queries_without_gpu():
+    import ctypes as C
+    from ppo_and_friends_b200 import _lib
+    lib = _lib.load()
+    desc = _lib.MlpDesc.make([376, 256, 256, 256, 17], "tanh")
+    offs, total = _lib.param_layout(desc, 17)
+    # W0 b0 W1 b1 W2 b2 W3 b3 log_std, every tensor on a 4-float boundary
+    assert offs[0] == 0 and offs[1] == 376 * 256 and all(o % 4 == 0 for o in offs)
+    assert total == offs[-1] + 20
+    assert lib.ppoaf_segscan_workspace_bytes(1 << 22) == (1 << 22) // 2048 * 64 + 64
+    cfg = _lib.UpdateCfg()
+    cfg.actor, cfg.critic = desc, _lib.MlpDesc.make([376, 256, 256, 256, 1], "tanh")
+    cfg.head, cfg.act_dim = _lib.HEAD_GAUSSIAN_TANH, 17
+    assert lib.ppoaf_update_workspace_bytes(C.byref(cfg), 512) > 512 * 256 * 4 * 12
+
+
+def test_no_cpu_fallback():
+    from ppo_and_friends_b200 import _lib
+    if torch.cuda.is_available():
+        pytest.skip("CUDA present")
+    with pytest.raises(_lib.PpoafError):
+        _lib.require_cuda()
+    from helpers import make_policy
+    from ppo_and_friends_b200.synthetic import make_rollout
+    with pytest.raises(_lib.PpoafError):
+        make_policy(make_rollout(0, 4, 2), device="cpu")
+
+
+def test_product_never_imports_oracle():
+    pkg = os.path.join(ROOT, "ppo_and_friends_b200")
+    for dirpath, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".h")):
+                src = open(os.path.join(dirpath, f)).read()
+                assert not re.search(r"^\s*(from|import)\s+oracle\b", src, re.M), f"{f} imports the oracle"
+                assert "/root/reference" not in src, f
+
+
+def test_permutation_protocol_matches_dataloader():
+    """Row U1: same global-RNG draws and the same indices as DataLoader(shuffle=True)."""
+    from torch.utils.data import DataLoader
+    from ppo_and_friends_b200.ppo import draw_minibatch_permutation
+
+    class DS(torch.utils.data.Dataset):
+        def __len__(self):
+            return 193
+
+        def __getitem__(self, i):
+            return i
+
+    for seed in (0, 1, 12345):
+        torch.manual_seed(seed)
+        loader = DataLoader(DS(), batch_size=64, shuffle=True)
+        ref = [torch.cat([b for b in loader]) for _ in range(3)]          # three epochs
+        state_after_ref = torch.random.get_rng_state()
+        torch.manual_seed(seed)
+        got = [draw_minibatch_permutation(193) for _ in range(3)]
+        for a, b in zip(ref, got):
+            assert torch.equal(a, b)
+        assert torch.equal(torch.random.get_rng_state(), state_after_ref)
+
+
+def test_hidden_sizes_and_key_stems():
+    from ppo_and_friends_b200.networks.feed_forward import hidden_sizes, layer_key_stems
+    assert hidden_sizes(64, 3) == [64, 64, 64] and hidden_sizes([32, 16], 9) == [32, 16] and hidden_sizes(0, 0) == []
+    with pytest.raises(ValueError):
+        hidden_sizes(0, 2)
+    assert layer_key_stems(3) == ["sequential_net.0", "sequential_net.2.0", "sequential_net.2.2", "sequential_net.3"]
+    assert layer_key_stems(1) == ["sequential_net.0", "sequential_net.3"] and layer_key_stems(0) == ["sequential_net.0"]
+
+
+def test_reference_init_order_matches_torch_sequential():
+    """Same torch seed -> same weights as building nn.Linear layers the way the reference does."""
+    from ppo_and_friends_b200.networks.feed_forward import reference_init
+    torch.manual_seed(3)
+    mine = reference_init([6, 8, 8, 2], 0.01)
+    torch.manual_seed(3)
+    ref = []
+    for i, (a, b) in enumerate(((6, 8), (8, 8), (8, 2))):
+        lin = torch.nn.Linear(a, b)
+        torch.nn.init.orthogonal_(lin.weight, 0.01 if i == 2 else np.sqrt(2))
+        torch.nn.init.constant_(lin.bias, 0.0)
+        ref.append(lin)
+    for (w, b), lin in zip(mine, ref):
+        assert torch.equal(w, lin.weight.detach()) and torch.equal(b, lin.bias.detach())
+
+
+def test_replay_driver_event_order():
+    """Terminated envs are closed before maxed ones at the same step; truncation beats termination."""
+    from ppo_and_friends_b200.synthetic import make_rollout, replay_rollout
+
+    class Rec:
+        def __init__(self):
+            self.calls = []
+
+        def add_episode_info(self, **kw):
+            self.calls.append(("add", kw["agent_id"]))
+
+        def end_episodes(self, agent_id, env_idxs, episode_lengths, terminal, ending_values, ending_rewards):
+            self.calls.append(("end", agent_id, tuple(int(e) for e in env_idxs), bool(terminal[0]), len(ending_values)))
+
+    ro = make_rollout(1, T=4, E=3, agents=("a", "b"), max_ts_per_ep=2, p_term=0.0, p_trunc=0.0)
+    ro.terminated[1, 0] = True
+    ro.terminated[2, 1] = True
+    ro.truncated[2, 1] = True                                            # both set: truncated wins
+    rec = Rec()
+    replay_rollout(lambda a: rec, ro)
+    ends = [c for c in rec.calls if c[0] == "end"]
+    assert ends[0] == ("end", "a", (0,), True, 1) and ends[1] == ("end", "b", (0,), True, 1)   # t=1 terminal
+    assert ends[2] == ("end", "a", (1, 2), False, 3)                                            # t=1 maxed, full [E] arrays
+    assert ends[4] == ("end", "a", (1,), False, 3)                                              # t=2: env1 truncated (not terminal)
+    assert ends[-1] == ("end", "b", (0, 1, 2), False, 3)                                        # rollout end closes every env
+
+
+GLOO_WORKER = r"""
+import os, sys
+import numpy as np, torch, torch.distributed as dist
+sys.path.insert(0, os.environ["PPOAF_ROOT"])
+from ppo_and_friends_b200.utils import mpi_utils
+dist.init_process_group("gloo", init_method="tcp://127.0.0.1:%s" % os.environ["PPOAF_PORT"],
+                        rank=int(os.environ["RANK"]), world_size=2)
+r = mpi_utils.get_rank()
+assert mpi_utils.get_num_procs() == 2
+p = torch.full((10,), float(r + 1))
+mpi_utils.broadcast_model_parameters(p)            # rank 0's parameters everywhere
+assert torch.equal(p, torch.ones(10))
+g = torch.arange(6, dtype=torch.float32) * (r + 1)
+mpi_utils.mpi_avg_gradients(g)                     # SUM; 1/R is applied by the Adam kernel
+assert torch.equal(g, torch.arange(6, dtype=torch.float32) * 3)
+assert abs(mpi_utils.mpi_avg(float(r)) - 0.5) < 1e-12
+assert np.allclose(mpi_utils.mpi_avg(np.array([r, 2.0 * r])), [0.5, 1.0])
+tr = torch.tensor([[r, 1.0, 2.0]], dtype=torch.float64)
+allg = mpi_utils.all_gather_cat(tr)
+assert allg.shape == (2, 1, 3) and allg[1, 0, 0] == 1.0 and allg[0, 0, 0] == 0.0
+s = torch.tensor([1.0, float(r)])
+mpi_utils.allreduce_sum_(s)
+assert torch.equal(s, torch.tensor([2.0, 1.0]))
+mpi_utils.barrier()
+print("rank", r, "ok")
+"""
+
+
+def test_comm_layer_gloo_world_size_2(tmp_path):
+    script = tmp_path / "worker.py"
+    script.write_text(GLOO_WORKER)
+    port = str(29000 + os.getpid() % 2000)
+    procs = []
+    for r in range(2):
+        env = dict(os.environ, RANK=str(r), PPOAF_ROOT=ROOT, PPOAF_PORT=port)
+        procs.append(subprocess.Popen([sys.executable, str(script)], env=env, stdout=subprocess.PIPE,
+                                      stderr=subprocess.STDOUT, text=True))
+    outs = [p.communicate(timeout=180)[0] for p in procs]
+    for p, o in zip(procs, outs):
+        assert p.returncode == 0, o
+    assert "rank 0 ok" in outs[0] and "rank 1 ok" in outs[1]
+
+
+def test_value_stat_merge_order_matches_allgather_semantics():
+    """Multi-rank value normaliser: pooling per-rank (mean, M2, n) triples in rank order equals the
+    reference's allgather + concatenate + np.mean/np.var (utils/stats.py:47-59)."""
+    from oracle.stats import OracleRunningMeanStd
+    rng = np.random.default_rng(2)
+    a, b = rng.normal(0, 2, 64).astype(np.float32), rng.normal(1, 1, 64).astype(np.float32)
+    ref = OracleRunningMeanStd()
+    ref.update(a, [b])
+
+    def triple(x):
+        x = x.astype(np.float64)
+        return x.mean(), ((x - x.mean()) ** 2).sum(), float(len(x))
+
+    (m1, s1, n1), (m2, s2, n2) = triple(a), triple(b)
+    n = n1 + n2
+    d = m2 - m1
+    mean, M2 = m1 + d * n2 / n, s1 + s2 + d * d * n1 * n2 / n
+    mine = OracleRunningMeanStd()
+    mine.integrate(mean, M2 / n, n)
+    assert abs(mine.mean - ref.mean) < 1e-6 and abs(mine.variance - ref.variance) < 1e-5 * ref.variance
