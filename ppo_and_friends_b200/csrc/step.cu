@@ -80,6 +80,11 @@ static void carve(const ppoaf_update_cfg* cfg, int max_batch, char* base, StepSc
         off += align_up(bytes, 256);
         return p;
     };
+    // control blocks first, at offsets that do not depend on the batch: they hold self-resetting tickets
+    // that must stay zero between launches, so no activation buffer may ever alias them
+    out->loss_ticket = reinterpret_cast<unsigned int*>(take(256));
+    out->optim_ws = take(optim_workspace_bytes(0));
+    out->loss_partials = reinterpret_cast<float*>(take(loss_workspace_bytes(max_batch, cfg->act_dim)));
     const ppoaf_mlp_desc* nets[2] = {&cfg->actor, &cfg->critic};
     NetScratch* ns[2] = {&out->actor, &out->critic};
     for (int k = 0; k < 2; ++k) {
@@ -89,9 +94,6 @@ static void carve(const ppoaf_update_cfg* cfg, int max_batch, char* base, StepSc
             ns[k]->dz[l] = reinterpret_cast<float*>(take(rows * nets[k]->dims[l] * sizeof(float)));
         }
     }
-    out->loss_partials = reinterpret_cast<float*>(take(loss_workspace_bytes(max_batch, cfg->act_dim)));
-    out->loss_ticket = reinterpret_cast<unsigned int*>(take(256));
-    out->optim_ws = take(optim_workspace_bytes(0));
     out->total = off;
 }
 
@@ -187,7 +189,7 @@ extern "C" int ppoaf_ppo_minibatch_grads(const ppoaf_update_cfg* cfg, const ppoa
     PPOAF_CHECK_ARG(b != nullptr && b->batch >= 1 && b->batch <= b->batch_size && b->n_flat > 0,
                     "ppoaf_ppo_minibatch_grads: bad batch sizes");
     if (b->batch == 1) return 0;  // the reference skips one-row minibatches (ppo.py:2305)
-    PPOAF_CHECK_ARG(b->workspace_bytes >= ppoaf_update_workspace_bytes(cfg, b->batch),
+    PPOAF_CHECK_ARG(b->workspace_bytes >= ppoaf_update_workspace_bytes(cfg, b->batch_size),
                     "ppoaf_ppo_minibatch_grads: workspace too small");
     PPOAF_CHECK_ARG(reinterpret_cast<uintptr_t>(b->workspace) % 256 == 0, "ppoaf_ppo_minibatch_grads: workspace must be 256-byte aligned");
     cudaStream_t s = (cudaStream_t)stream;
@@ -195,7 +197,7 @@ extern "C" int ppoaf_ppo_minibatch_grads(const ppoaf_update_cfg* cfg, const ppoa
     if (get_side_stream(&ss)) return 1;
 
     StepScratch sc;
-    carve(cfg, b->batch, reinterpret_cast<char*>(b->workspace), &sc);
+    carve(cfg, b->batch_size, reinterpret_cast<char*>(b->workspace), &sc);  // layout fixed by the nominal B
     const bool gaussian = cfg->head == PPOAF_HEAD_GAUSSIAN_TANH;
     int64_t off_a[2 * PPOAF_MAX_LAYERS + 1], off_c[2 * PPOAF_MAX_LAYERS + 1];
     const int64_t n_actor = param_layout(&cfg->actor, gaussian ? cfg->act_dim : 0, off_a);
@@ -262,7 +264,7 @@ extern "C" int ppoaf_ppo_minibatch_apply(const ppoaf_update_cfg* cfg, const ppoa
     cudaStream_t s = (cudaStream_t)stream;
     if (b->batch == 1) return launch_advance_cursor(b->mb_cursor, s);
     StepScratch sc;
-    carve(cfg, b->batch, reinterpret_cast<char*>(b->workspace), &sc);
+    carve(cfg, b->batch_size, reinterpret_cast<char*>(b->workspace), &sc);
     const bool gaussian = cfg->head == PPOAF_HEAD_GAUSSIAN_TANH;
     const int64_t n_actor = param_layout(&cfg->actor, gaussian ? cfg->act_dim : 0, nullptr);
     const int64_t n_critic = param_layout(&cfg->critic, 0, nullptr);
