@@ -188,10 +188,12 @@ class HotPath:
         return 64 * self.w["epochs"]
 
     def launches_per_step(self):
-        la, lc = 4, 4                                      # Linear layers per net (hidden_depth 3 + output)
-        per_mb = la + lc + 1 + (2 * la - 1) + (2 * lc - 1) + 2
-        per_epoch = 2 + per_mb * self.n_mb
-        finalize = 1 + 8 + 1
+        """Kernels of libppoaf_b200.so launched per step (torch's own fills / copies are not counted)."""
+        world = torch.distributed.get_world_size() if torch.distributed.is_initialized() else 1
+        layers = 4                                         # Linear layers per net (hidden_depth 3 + output)
+        per_mb = layers + 1 + layers + 1 + (1 if world > 1 else 0)   # grouped fwd, loss, grouped bwd, [norm,] adam
+        per_epoch = 2 + per_mb * self.n_mb                 # epoch_prepare + value_stats_sequence
+        finalize = 1 + 8 + 1                               # flat map, 8 field gathers, segmented scan
         return finalize + per_epoch * self.w["epochs"]
 
 

@@ -135,7 +135,8 @@ typedef struct {
     int32_t normalize_adv;        /* ppo.py:2325-2333                                               */
     int32_t normalize_values;     /* ppo.py:2299-2303                                               */
     int32_t vf_clip_enabled;      /* value clip on (clip value itself is PPOAF_HP_VF_CLIP)          */
-    int32_t reserved[2];
+    int32_t world_size;           /* ranks whose gradients the caller all-reduces between grads/apply */
+    int32_t reserved[1];
     float   min_std;              /* GaussianDistribution min_std (networks/distributions.py:453)   */
     float   reserved_f[3];
 } ppoaf_update_cfg;

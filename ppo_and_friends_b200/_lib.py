@@ -39,7 +39,7 @@ class MlpDesc(C.Structure):
 class UpdateCfg(C.Structure):
     _fields_ = [("actor", MlpDesc), ("critic", MlpDesc), ("head", C.c_int32), ("act_dim", C.c_int32),
                 ("use_huber", C.c_int32), ("normalize_adv", C.c_int32), ("normalize_values", C.c_int32),
-                ("vf_clip_enabled", C.c_int32), ("reserved", C.c_int32 * 2), ("min_std", C.c_float),
+                ("vf_clip_enabled", C.c_int32), ("world_size", C.c_int32), ("reserved", C.c_int32 * 1), ("min_std", C.c_float),
                 ("reserved_f", C.c_float * 3)]
 
 

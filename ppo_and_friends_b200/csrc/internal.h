@@ -4,13 +4,28 @@
 
 namespace ppoaf {
 
-// mlp.cu
-void linear_forward(const float* X, int ldx, const int64_t* idx, const int32_t* cursor, int cursor_stride,
-                    const float* W, const float* b, float* Y, int rows, int in, int out, int act, cudaStream_t s);
-void linear_backward_x(const float* dZ, const float* W, const float* Xact, float* dX, int rows, int in, int out,
-                       int act, cudaStream_t s);
-void linear_backward_w(const float* dZ, const float* X, int ldx, const int64_t* idx, const int32_t* cursor,
-                       int cursor_stride, float* dW, float* db, int rows, int in, int out, cudaStream_t s);
+// mlp.cu — grouped GEMM launches (all GEMMs of one phase of the minibatch step in ONE launch)
+struct GroupedGemmArgs;
+struct GemmGroup {
+    GroupedGemmArgs* args;      // owned
+    int n_tiles;
+    GemmGroup();
+    ~GemmGroup();
+    GemmGroup(const GemmGroup&) = delete;
+    GemmGroup& operator=(const GemmGroup&) = delete;
+    // Y[rows, out] = act(X[idx][rows, in] W^T + b)
+    void add_forward(const float* X, int ldx, const int64_t* idx, const float* W, const float* b, float* Y, int rows,
+                     int in, int out, int act);
+    // dX[rows, in] = (dZ[rows, out] W[out, in]) * act'(Xact[rows, in])
+    void add_backward_x(const float* dZ, const float* W, const float* Xact, float* dX, int rows, int in, int out, int act);
+    // dW[out, in] = dZ[rows, out]^T X[idx][rows, in]; db[out] = column sums of dZ; sq_out[tile] = tile sum of squares
+    // returns the number of sum-of-squares slots (tiles) this problem writes
+    int add_backward_w(const float* dZ, const float* X, int ldx, const int64_t* idx, float* dW, float* db, int rows,
+                       int in, int out, double* sq_out);
+    int launch(const int32_t* cursor, int cursor_stride, cudaStream_t s);
+};
+int backward_w_tiles(int in, int out);
+void configure_gemm_kernels();
 int64_t param_layout(const ppoaf_mlp_desc* net, int32_t log_std_dim, int64_t* offsets);
 int check_mlp_desc(const ppoaf_mlp_desc* net, const char* who);
 
@@ -35,7 +50,8 @@ struct LossArgs {
     float* d_actor_out;          // [batch, pred]
     float* d_critic_out;         // [batch]  (or [2, batch] scratch when vf_clip is on)
     float* d_log_std;            // [act_dim] inside grads
-    float* partials;             // workspace: [n_blocks, kLossScalars + act_dim]
+    double* sq_log_std;          // one slot: sum of squares of d_log_std (nullable)
+    float* partials;             // workspace
     unsigned int* ticket;        // zero-initialised, self-resetting
     int head, act_dim, pred_dim;
     int use_huber, normalize_adv, normalize_values, vf_clip_enabled;
@@ -45,9 +61,12 @@ size_t loss_workspace_bytes(int max_batch, int act_dim);
 int launch_ppo_loss(const LossArgs& a, cudaStream_t s);
 
 // optim.cu
-size_t optim_workspace_bytes(int64_t n_total);
-int launch_advance_cursor(int32_t* mb_cursor, cudaStream_t s);
+size_t optim_workspace_bytes();
+// sq_a / sq_c: per-network sum-of-squares slots already produced by the backward-w epilogues (n_sq_* > 0), or
+// null -> a norm pass over the (all-reduced) gradients is run first.
 int launch_clip_adam(float* params, const float* grads, float* m, float* v, int64_t* adam_step, int32_t* mb_cursor,
-                     const double* hparams, int64_t n_actor, int64_t n_critic, void* workspace, cudaStream_t s);
+                     const double* hparams, int64_t n_actor, int64_t n_critic, const double* sq_a, int n_sq_a,
+                     const double* sq_c, int n_sq_c, void* workspace, cudaStream_t s);
+int launch_advance_cursor(int32_t* mb_cursor, cudaStream_t s);
 
 }  // namespace ppoaf

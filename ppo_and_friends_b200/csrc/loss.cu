@@ -12,11 +12,16 @@
 
 namespace ppoaf {
 
-constexpr int kLossThreads = 128;
 constexpr int kMaxAct = 64;
+constexpr int kG = 8;                       // lanes that share one sample (each owns dims l, l+8, ...)
+constexpr int kPerLane = kMaxAct / kG;      // 8
+constexpr int kLossThreads = 256;           // 32 samples per CTA
+constexpr int kSamplesPerBlock = kLossThreads / kG;
 enum { LS_ACTOR = 0, LS_CRITIC, LS_CRITIC_CLIPPED, LS_ENTROPY, LS_KL, LS_BAD_RATIO, LS_BAD_VALUE, kLossScalars };
+constexpr int kPartialStride = kLossScalars + kMaxAct;
 
 constexpr float kLogSqrt2Pi = 0.91893853320467274178f;
+constexpr float kCatEps = 1.1920928955078125e-07f;   // torch.finfo(float32).eps
 
 __device__ __forceinline__ float softplus_torch(float x) { return x > 20.f ? x : log1pf(expf(x)); }
 
@@ -32,13 +37,27 @@ __device__ __forceinline__ float critic_term(float v, float target, int use_hube
     return d * d;
 }
 
+// sum / max over the kG lanes that share a sample (lanes are contiguous inside a warp)
+__device__ __forceinline__ float group_sum(float v) {
+#pragma unroll
+    for (int o = kG / 2; o > 0; o >>= 1) v += __shfl_xor_sync(kFull, v, o);
+    return v;
+}
+__device__ __forceinline__ float group_max(float v) {
+#pragma unroll
+    for (int o = kG / 2; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(kFull, v, o));
+    return v;
+}
+
 __global__ void __launch_bounds__(kLossThreads) ppo_loss_kernel(const LossArgs a) {
     __shared__ float s_sd[kMaxAct], s_dsd[kMaxAct];
-    __shared__ double s_red[kLossThreads / 32][kLossScalars + kMaxAct];
+    __shared__ double s_red[kLossThreads / 32][kPartialStride];
+    __shared__ double s_tot[kPartialStride];
     __shared__ bool s_last;
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const int i = blockIdx.x * kLossThreads + tid;
+    const int gl = tid & (kG - 1);                                   // lane inside the sample group
+    const int i = blockIdx.x * kSamplesPerBlock + tid / kG;          // sample of this group
     const bool live = i < a.batch;
     const int cur = *a.cursor;
     const int64_t* idx = a.perm + int64_t(cur) * a.batch_size;
@@ -49,7 +68,7 @@ __global__ void __launch_bounds__(kLossThreads) ppo_loss_kernel(const LossArgs a
     const bool gaussian = a.head == PPOAF_HEAD_GAUSSIAN_TANH;
 
     if (gaussian && tid < a.act_dim) {
-        // std = max(softplus(log_std), min_std)  (distributions.py:514-515); d std / d log_std
+        // std = max(softplus(log_std), min_std)  (distributions.py:514-515) and d std / d log_std
         const float ls = a.log_std[tid];
         const float sp = softplus_torch(ls);
         s_sd[tid] = fmaxf(sp, a.min_std);
@@ -58,183 +77,227 @@ __global__ void __launch_bounds__(kLossThreads) ppo_loss_kernel(const LossArgs a
     }
     __syncthreads();
 
-    double sc[kLossScalars];
+    float sc[kLossScalars];
 #pragma unroll
-    for (int k = 0; k < kLossScalars; ++k) sc[k] = 0.0;
-    float dsd_local[kMaxAct];  // only the first act_dim entries are used (Gaussian)
+    for (int k = 0; k < kLossScalars; ++k) sc[k] = 0.f;
+    float dsd[kPerLane];                                             // d loss / d std for dims gl + 8k of this sample
+#pragma unroll
+    for (int k = 0; k < kPerLane; ++k) dsd[k] = 0.f;
 
-    if (live) {
-        const int64_t j = idx[i];
-        float adv = a.advantages[j];
-        if (a.normalize_adv) adv = (adv - a.mb_adv_stats[2 * cur]) / a.mb_adv_stats[2 * cur + 1];
-        const float lp_old = a.log_probs[j];
-        float target = a.rewards_to_go[j];
-        if (a.normalize_values) target = (target - a.mb_val_stats[2 * cur]) / a.mb_val_stats[2 * cur + 1];
-        const float v = a.critic_out[i];
-        a.values[j] = v;                                         // dataset.values[batch_idxs] = values (ppo.py:2340)
-        bool bad_value = isnan(v);
+    // every lane of the group runs the (cheap) per-sample scalar math so the shuffles stay convergent
+    const int64_t j = live ? idx[i] : 0;
+    float adv = live ? a.advantages[j] : 0.f;
+    if (a.normalize_adv) adv = (adv - a.mb_adv_stats[2 * cur]) / a.mb_adv_stats[2 * cur + 1];
+    const float lp_old = live ? a.log_probs[j] : 0.f;
+    float target = live ? a.rewards_to_go[j] : 0.f;
+    if (a.normalize_values) target = (target - a.mb_val_stats[2 * cur]) / a.mb_val_stats[2 * cur + 1];
+    const float v = live ? a.critic_out[i] : 0.f;
+    if (live && gl == 0) a.values[j] = v;                            // dataset.values[batch_idxs] = values (ppo.py:2340)
+    float bad_value = isnan(v) ? 1.f : 0.f;
 
-        // ---------------- log-prob and entropy ----------------
-        float lp = 0.f, ent = 0.f;
-        const float* pred = a.actor_out + int64_t(i) * a.pred_dim;
-        float pt[kMaxAct], lg[kMaxAct];  // Categorical: renormalised probs and clamped logs
-        float cat_S = 1.f;
-        int action = 0;
-        if (gaussian) {
-            const float* x = reinterpret_cast<const float*>(a.raw_actions) + j * a.act_dim;
-            float nsum = 0.f, slog = 0.f, ensum = 0.f, eslog = 0.f;
-            for (int d = 0; d < a.act_dim; ++d) {
-                const float mu = pred[d], sd = s_sd[d], z = x[d] - mu;
-                bad_value |= isnan(mu);
+    const float* pred = a.actor_out + int64_t(live ? i : 0) * a.pred_dim;
+    float* dpred = a.d_actor_out + int64_t(live ? i : 0) * a.pred_dim;
+    float lp = 0.f, ent = 0.f;
+
+    if (gaussian) {
+        const float* x = reinterpret_cast<const float*>(a.raw_actions) + j * a.act_dim;
+        float mu[kPerLane], z[kPerLane], on[kPerLane], one[kPerLane], thm[kPerLane];
+        float nsum = 0.f, slog = 0.f, ensum = 0.f, eslog = 0.f;
+#pragma unroll
+        for (int k = 0; k < kPerLane; ++k) {
+            const int d = gl + k * kG;
+            mu[k] = z[k] = on[k] = one[k] = thm[k] = 0.f;
+            if (d < a.act_dim && live) {
+                const float sd = s_sd[d], xd = x[d];
+                mu[k] = pred[d];
+                z[k] = xd - mu[k];
+                bad_value = fmaxf(bad_value, isnan(mu[k]) ? 1.f : 0.f);
                 const float lsd = logf(sd);
-                const float nl = -(z * z) / (2.f * (sd * sd)) - lsd - kLogSqrt2Pi;
+                const float nl = -(z[k] * z[k]) / (2.f * (sd * sd)) - lsd - kLogSqrt2Pi;   // Normal.log_prob
                 nsum += fminf(fmaxf(nl, -100.f), 100.f);
-                const float th = tanhf(x[d]);
+                on[k] = (nl >= -100.f && nl <= 100.f) ? 1.f : 0.f;
+                const float th = tanhf(xd);
                 slog += logf(fmaxf(1.f - th * th, 1e-6f));
-                const float nle = -lsd - kLogSqrt2Pi;               // log N(mu; mu, sd)
+                const float nle = -lsd - kLogSqrt2Pi;                                     // log N(mu; mu, sd)
                 ensum += fminf(fmaxf(nle, -100.f), 100.f);
-                const float thm = tanhf(mu);
-                eslog += logf(fmaxf(1.f - thm * thm, 1e-6f));
+                one[k] = (nle >= -100.f && nle <= 100.f) ? 1.f : 0.f;
+                thm[k] = tanhf(mu[k]);
+                eslog += logf(fmaxf(1.f - thm[k] * thm[k], 1e-6f));
             }
-            lp = nsum - slog;
-            ent = -(ensum - eslog);                                   // entropy = -log_prob(mean) (:694)
-        } else {
-            const int n = a.pred_dim;
-            action = int(reinterpret_cast<const int64_t*>(a.raw_actions)[j * a.act_dim]);
-            float mx = pred[0];
-            for (int c = 1; c < n; ++c) mx = fmaxf(mx, pred[c]);
-            float se = 0.f;
-            for (int c = 0; c < n; ++c) { pt[c] = expf(pred[c] - mx); se += pt[c]; bad_value |= isnan(pred[c]); }
-            float S = 0.f;
-            for (int c = 0; c < n; ++c) { pt[c] = pt[c] / se; S += pt[c]; }   // softmax inside the actor (:1045)
-            cat_S = S;
-            const float ceps = 1.1920928955078125e-07f;                        // torch.finfo(float32).eps
-            float h = 0.f;
-            for (int c = 0; c < n; ++c) {
-                lg[c] = pt[c];                                                 // keep raw softmax prob for backward
-                const float pn = pt[c] / S;                                    // Categorical renormalises probs
-                pt[c] = pn;
-                const float q = fminf(fmaxf(pn, ceps), 1.f - ceps);
-                const float l = logf(q);
-                h += pn * l;
-                if (c == action) lp = l;
-            }
-            ent = -h;
         }
-
-        // ---------------- surrogate ----------------
+        lp = group_sum(nsum) - group_sum(slog);
+        ent = -(group_sum(ensum) - group_sum(eslog));                 // entropy = -log_prob(mean) (:694)
         const float ratio = expf(lp - lp_old);
-        const float s1 = ratio * adv;
-        const float s2 = fminf(fmaxf(ratio, clip_lo), clip_hi) * adv;
-        const bool bad_ratio = isnan(ratio) || isinf(ratio);
-        sc[LS_ACTOR] = double(-fminf(s1, s2));
-        sc[LS_KL] = double(lp_old - lp);
-        sc[LS_ENTROPY] = double(ent);
-        sc[LS_BAD_RATIO] = bad_ratio ? 1.0 : 0.0;
-        sc[LS_BAD_VALUE] = bad_value ? 1.0 : 0.0;
-        // d(-min(s1,s2))/d lp: gradient flows through s1 when s1 <= s2 (ties: both branches carry half
-        // and the clamp passes its half exactly when rho is inside the clip range, which a tie implies)
+        const float s1 = ratio * adv, s2 = fminf(fmaxf(ratio, clip_lo), clip_hi) * adv;
+        // d(-min(s1,s2))/d lp flows through s1 when s1 <= s2 (on a tie both branches carry half and the
+        // clamp passes its half exactly when rho is inside the clip range, which the tie implies)
         const float g_lp = (s1 <= s2) ? -adv * ratio * inv_b : 0.f;
-        const float g_ent = -w_ent * inv_b;                              // dL/dH_i
-
-        // ---------------- backward through the head ----------------
-        float* dpred = a.d_actor_out + int64_t(i) * a.pred_dim;
-        if (gaussian) {
-            const float* x = reinterpret_cast<const float*>(a.raw_actions) + j * a.act_dim;
-            for (int d = 0; d < a.act_dim; ++d) {
-                const float mu = pred[d], sd = s_sd[d], z = x[d] - mu;
-                const float var = sd * sd;
-                const float nl = -(z * z) / (2.f * var) - logf(sd) - kLogSqrt2Pi;
-                const float on = (nl >= -100.f && nl <= 100.f) ? 1.f : 0.f;
-                const float nle = -logf(sd) - kLogSqrt2Pi;
-                const float one = (nle >= -100.f && nle <= 100.f) ? 1.f : 0.f;
-                const float thm = tanhf(mu);
-                const float tmask = (1.f - thm * thm >= 1e-6f) ? 1.f : 0.f;
-                // dlp/dmu = z/var ; dH/dmu = -2 tanh(mu)
-                dpred[d] = g_lp * on * (z / var) + g_ent * tmask * (-2.f * thm);
-                // dlp/dsd = z^2/sd^3 - 1/sd ; dH/dsd = 1/sd
-                dsd_local[d] = g_lp * on * ((z * z) / (var * sd) - 1.f / sd) + g_ent * one * (1.f / sd);
-            }
-        } else {
-            const int n = a.pred_dim;
-            const float ceps = 1.1920928955078125e-07f;
-            // G_c = dL/dpt_c ; pt = p / S ; p = softmax(z)
-            float G[kMaxAct];
-            float gdotp = 0.f;
-            for (int c = 0; c < n; ++c) {
-                const float pn = pt[c];
-                const float q = fminf(fmaxf(pn, ceps), 1.f - ceps);
-                const float mask = (pn >= ceps && pn <= 1.f - ceps) ? 1.f : 0.f;
-                const float l = logf(q);
-                // L depends on pt_c through lg_c (log-prob of the action and the p*log p sum) and directly (H)
-                const float dlg = (c == action ? g_lp : 0.f) + g_ent * (-pn);
-                G[c] = g_ent * (-l) + dlg * mask / q;
-                gdotp += G[c] * lg[c];                                       // lg[] holds the raw softmax probs
-            }
-            float dp[kMaxAct];
-            float dpdotp = 0.f;
-            for (int c = 0; c < n; ++c) {
-                dp[c] = G[c] / cat_S - gdotp / (cat_S * cat_S);
-                dpdotp += dp[c] * lg[c];
-            }
-            for (int c = 0; c < n; ++c) dpred[c] = lg[c] * (dp[c] - dpdotp);
+        const float g_ent = -w_ent * inv_b;                           // dL/dH_i
+        if (gl == 0 && live) {
+            sc[LS_ACTOR] = -fminf(s1, s2);
+            sc[LS_KL] = lp_old - lp;
+            sc[LS_ENTROPY] = ent;
+            sc[LS_BAD_RATIO] = (isnan(ratio) || isinf(ratio)) ? 1.f : 0.f;
         }
+#pragma unroll
+        for (int k = 0; k < kPerLane; ++k) {
+            const int d = gl + k * kG;
+            if (d < a.act_dim && live) {
+                const float sd = s_sd[d], var = sd * sd;
+                const float tmask = (1.f - thm[k] * thm[k] >= 1e-6f) ? 1.f : 0.f;
+                // dlp/dmu = z/var ; dH/dmu = -2 tanh(mu)
+                dpred[d] = g_lp * on[k] * (z[k] / var) + g_ent * tmask * (-2.f * thm[k]);
+                // dlp/dsd = z^2/sd^3 - 1/sd ; dH/dsd = 1/sd
+                dsd[k] = g_lp * on[k] * ((z[k] * z[k]) / (var * sd) - 1.f / sd) + g_ent * one[k] * (1.f / sd);
+            }
+        }
+    } else {
+        const int n = a.pred_dim;
+        const int action = live ? int(reinterpret_cast<const int64_t*>(a.raw_actions)[j * a.act_dim]) : 0;
+        float p[kPerLane], pn[kPerLane], lg[kPerLane];
+        float mx = -INFINITY;
+#pragma unroll
+        for (int k = 0; k < kPerLane; ++k) {
+            const int c = gl + k * kG;
+            p[k] = (c < n) ? pred[c] : -INFINITY;
+            if (c < n) bad_value = fmaxf(bad_value, isnan(p[k]) ? 1.f : 0.f);
+            mx = fmaxf(mx, p[k]);
+        }
+        mx = group_max(mx);
+        float se = 0.f;
+#pragma unroll
+        for (int k = 0; k < kPerLane; ++k) {
+            const int c = gl + k * kG;
+            p[k] = (c < n) ? expf(p[k] - mx) : 0.f;
+            se += p[k];
+        }
+        se = group_sum(se);
+        float S = 0.f;
+#pragma unroll
+        for (int k = 0; k < kPerLane; ++k) { p[k] = p[k] / se; S += p[k]; }       // softmax inside the actor (:1045)
+        S = group_sum(S);
+        float h = 0.f, lpa = 0.f;
+#pragma unroll
+        for (int k = 0; k < kPerLane; ++k) {
+            const int c = gl + k * kG;
+            pn[k] = p[k] / S;                                                       // Categorical renormalises probs
+            lg[k] = logf(fminf(fmaxf(pn[k], kCatEps), 1.f - kCatEps));
+            if (c < n) { h += pn[k] * lg[k]; if (c == action) lpa = lg[k]; }
+        }
+        lp = group_sum(lpa);
+        ent = -group_sum(h);
+        const float ratio = expf(lp - lp_old);
+        const float s1 = ratio * adv, s2 = fminf(fmaxf(ratio, clip_lo), clip_hi) * adv;
+        const float g_lp = (s1 <= s2) ? -adv * ratio * inv_b : 0.f;
+        const float g_ent = -w_ent * inv_b;
+        if (gl == 0 && live) {
+            sc[LS_ACTOR] = -fminf(s1, s2);
+            sc[LS_KL] = lp_old - lp;
+            sc[LS_ENTROPY] = ent;
+            sc[LS_BAD_RATIO] = (isnan(ratio) || isinf(ratio)) ? 1.f : 0.f;
+        }
+        // G_c = dL/d pn_c ; pn = p / S ; p = softmax(z)
+        float G[kPerLane];
+        float gdotp = 0.f;
+#pragma unroll
+        for (int k = 0; k < kPerLane; ++k) {
+            const int c = gl + k * kG;
+            G[k] = 0.f;
+            if (c < n) {
+                const float q = fminf(fmaxf(pn[k], kCatEps), 1.f - kCatEps);
+                const float mask = (pn[k] >= kCatEps && pn[k] <= 1.f - kCatEps) ? 1.f : 0.f;
+                const float dlg = (c == action ? g_lp : 0.f) + g_ent * (-pn[k]);
+                G[k] = g_ent * (-lg[k]) + dlg * mask / q;
+                gdotp += G[k] * p[k];
+            }
+        }
+        gdotp = group_sum(gdotp);
+        float dpdotp = 0.f;
+#pragma unroll
+        for (int k = 0; k < kPerLane; ++k) {
+            G[k] = G[k] / S - gdotp / (S * S);                                      // dL/dp_c
+            dpdotp += G[k] * p[k];
+        }
+        dpdotp = group_sum(dpdotp);
+#pragma unroll
+        for (int k = 0; k < kPerLane; ++k) {
+            const int c = gl + k * kG;
+            if (c < n && live) dpred[c] = p[k] * (G[k] - dpdotp);
+        }
+    }
 
-        // ---------------- critic ----------------
+    // ---------------- critic ----------------
+    if (gl == 0 && live) {
         float dv1;
-        const float l1 = critic_term(v, target, a.use_huber, dv1);
-        sc[LS_CRITIC] = double(l1);
+        sc[LS_CRITIC] = critic_term(v, target, a.use_huber, dv1);
         if (a.vf_clip_enabled) {
             const float vc = fminf(fmaxf(v, -vf_clip), vf_clip);
             float dv2;
-            const float l2 = critic_term(vc, target, a.use_huber, dv2);
-            sc[LS_CRITIC_CLIPPED] = double(l2);
+            sc[LS_CRITIC_CLIPPED] = critic_term(vc, target, a.use_huber, dv2);
             const float pass = (v >= -vf_clip && v <= vf_clip) ? 1.f : 0.f;
-            a.d_critic_out[i] = dv1 * inv_b;                                 // combined by vf_select_kernel
+            a.d_critic_out[i] = dv1 * inv_b;                                         // combined by vf_select_kernel
             a.d_critic_out[a.batch + i] = dv2 * pass * inv_b;
         } else {
             a.d_critic_out[i] = dv1 * inv_b;
         }
-    } else if (gaussian) {
-        for (int d = 0; d < a.act_dim; ++d) dsd_local[d] = 0.f;
     }
+    const float bad_any = group_max(bad_value);
+    sc[LS_BAD_VALUE] = (live && gl == 0) ? bad_any : 0.f;
 
     // ---------------- CTA reduction (fp64, fixed order) ----------------
     const int n_extra = gaussian ? a.act_dim : 0;
 #pragma unroll
     for (int k = 0; k < kLossScalars; ++k) {
-        const double w = warp_sum(sc[k]);
+        const double w = warp_sum(double(sc[k]));
         if (lane == 0) s_red[warp][k] = w;
     }
-    for (int d = 0; d < n_extra; ++d) {
-        const double w = warp_sum(double(live ? dsd_local[d] : 0.f));
-        if (lane == 0) s_red[warp][kLossScalars + d] = w;
+    if (gaussian) {
+#pragma unroll
+        for (int k = 0; k < kPerLane; ++k) {
+            double w = double(dsd[k]);                   // sum the 4 sample-groups of the warp: lanes l, l+8, l+16, l+24
+            w += __shfl_xor_sync(kFull, w, 8);
+            w += __shfl_xor_sync(kFull, w, 16);
+            if (lane < kG) s_red[warp][kLossScalars + lane + k * kG] = w;
+        }
     }
     __syncthreads();
     const int n_vals = kLossScalars + n_extra;
     double* part = reinterpret_cast<double*>(a.partials);
     if (tid < n_vals) {
         double t = 0.0;
+#pragma unroll
         for (int w = 0; w < kLossThreads / 32; ++w) t += s_red[w][tid];
-        part[size_t(blockIdx.x) * (kLossScalars + kMaxAct) + tid] = t;
+        part[size_t(blockIdx.x) * kPartialStride + tid] = t;
     }
     __threadfence();
     __syncthreads();
-    if (tid == 0) {
-        const unsigned int done = atomicAdd(a.ticket, 1u);
-        s_last = done == gridDim.x - 1;
-    }
+    if (tid == 0) s_last = atomicAdd(a.ticket, 1u) == gridDim.x - 1;
     __syncthreads();
     if (!s_last) return;
     __threadfence();
 
     // ---------------- last CTA: totals -> d(log_std), epoch statistics, value-clip weights -----------
-    __shared__ double s_tot[kLossScalars + kMaxAct];
+    double my_sq = 0.0;
     if (tid < n_vals) {
         double t = 0.0;
-        for (unsigned b = 0; b < gridDim.x; ++b) t += __ldcg(&part[size_t(b) * (kLossScalars + kMaxAct) + tid]);
+        for (unsigned b = 0; b < gridDim.x; ++b) t += __ldcg(&part[size_t(b) * kPartialStride + tid]);
         s_tot[tid] = t;
-        if (tid >= kLossScalars) a.d_log_std[tid - kLossScalars] = float(t) * s_dsd[tid - kLossScalars];
+        if (tid >= kLossScalars) {
+            const float gls = float(t) * s_dsd[tid - kLossScalars];
+            a.d_log_std[tid - kLossScalars] = gls;
+            my_sq = double(gls) * double(gls);
+        }
+    }
+    if (a.sq_log_std) {                                    // sum of squares of d(log_std) for the gradient-norm clip
+        __shared__ double s_sq[kLossThreads / 32];
+        const double w = warp_sum(my_sq);
+        if (lane == 0) s_sq[warp] = w;
+        __syncthreads();
+        if (tid == 0) {
+            double t = 0.0;
+            for (int k = 0; k < kLossThreads / 32; ++k) t += s_sq[k];
+            *a.sq_log_std = t;
+        }
     }
     __syncthreads();
     if (tid == 0) {
@@ -248,7 +311,7 @@ __global__ void __launch_bounds__(kLossThreads) ppo_loss_kernel(const LossArgs a
             float w1 = 1.f, w2 = 0.f;
             if (clipped_mean > critic_mean) { w1 = 0.f; w2 = 1.f; critic_mean = clipped_mean; }
             else if (clipped_mean == critic_mean) { w1 = 0.5f; w2 = 0.5f; }
-            float* wsel = reinterpret_cast<float*>(part + size_t(gridDim.x) * (kLossScalars + kMaxAct));
+            float* wsel = reinterpret_cast<float*>(part + size_t(gridDim.x) * kPartialStride);
             wsel[0] = w1; wsel[1] = w2;
         }
         a.epoch_stats[PPOAF_ST_ACTOR_LOSS] += double(actor_mean);
@@ -269,20 +332,20 @@ __global__ void vf_select_kernel(float* __restrict__ d_critic_out, int batch, co
 }
 
 size_t loss_workspace_bytes(int max_batch, int /*act_dim*/) {
-    const size_t blocks = size_t((max_batch + kLossThreads - 1) / kLossThreads);
-    return align_up(blocks * (kLossScalars + kMaxAct) * sizeof(double) + 16, 256);
+    const size_t blocks = size_t((max_batch + kSamplesPerBlock - 1) / kSamplesPerBlock);
+    return align_up(blocks * kPartialStride * sizeof(double) + 16, 256);
 }
 
 int launch_ppo_loss(const LossArgs& a, cudaStream_t s) {
     PPOAF_CHECK_ARG(a.act_dim >= 1 && a.act_dim <= kMaxAct && a.pred_dim >= 1 && a.pred_dim <= kMaxAct,
                     "ppo loss: act_dim / prediction width must be in [1, %d]", kMaxAct);
     PPOAF_CHECK_ARG(a.batch >= 2, "ppo loss: minibatches of fewer than 2 rows are skipped by the caller");
-    const int blocks = (a.batch + kLossThreads - 1) / kLossThreads;
+    const int blocks = (a.batch + kSamplesPerBlock - 1) / kSamplesPerBlock;
     ppo_loss_kernel<<<blocks, kLossThreads, 0, s>>>(a);
     PPOAF_CHECK_LAUNCH("ppo_loss_kernel");
     if (a.vf_clip_enabled) {
         const float* wsel = reinterpret_cast<const float*>(reinterpret_cast<const double*>(a.partials) +
-                                                           size_t(blocks) * (kLossScalars + kMaxAct));
+                                                           size_t(blocks) * kPartialStride);
         vf_select_kernel<<<(a.batch + 255) / 256, 256, 0, s>>>(a.d_critic_out, a.batch, wsel);
         PPOAF_CHECK_LAUNCH("vf_select_kernel");
     }

@@ -5,56 +5,64 @@
 
 namespace ppoaf {
 
-constexpr int kBM = 32, kBN = 64, kBK = 16;
-
 static inline bool vec4_ok(const float* p, int ld, int contig_extent) {
     return (reinterpret_cast<uintptr_t>(p) % 16 == 0) && (ld % 4 == 0) && (contig_extent % 4 == 0);
 }
 
-template <bool ARC, bool BRC, int EPI>
-static void launch_gemm(const GemmArgs& g, bool va, bool vb, cudaStream_t s) {
-    const dim3 grid((g.N + kBN - 1) / kBN, (g.M + kBM - 1) / kBM);
-    const int threads = (kBM / 4) * (kBN / 4);
-    if (va && vb)
-        gemm_tile_kernel<kBM, kBN, kBK, ARC, BRC, 4, 4, EPI><<<grid, threads, 0, s>>>(g);
-    else if (va)
-        gemm_tile_kernel<kBM, kBN, kBK, ARC, BRC, 4, 1, EPI><<<grid, threads, 0, s>>>(g);
-    else if (vb)
-        gemm_tile_kernel<kBM, kBN, kBK, ARC, BRC, 1, 4, EPI><<<grid, threads, 0, s>>>(g);
-    else
-        gemm_tile_kernel<kBM, kBN, kBK, ARC, BRC, 1, 1, EPI><<<grid, threads, 0, s>>>(g);
+// Called from ppoaf_runtime_init so that no attribute call happens inside a stream capture.
+void configure_gemm_kernels() {
+    cudaFuncSetAttribute(grouped_gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, int(kGemmSmemBytes));
 }
 
-// Y[rows, out] = act(X[idx][rows, in] W^T + b)
-void linear_forward(const float* X, int ldx, const int64_t* idx, const int32_t* cursor, int cursor_stride,
-                    const float* W, const float* b, float* Y, int rows, int in, int out, int act, cudaStream_t s) {
-    GemmArgs g{};
-    g.A = X; g.lda = ldx; g.B = W; g.ldb = in; g.C = Y; g.ldc = out;
-    g.M = rows; g.N = out; g.K = in;
-    g.idxA = idx; g.idxB = nullptr; g.cursor = cursor; g.cursor_stride = cursor_stride;
-    g.bias = b; g.act = act;
-    launch_gemm<true, true, EPI_FWD>(g, vec4_ok(X, ldx, in), vec4_ok(W, in, in), s);
+GemmGroup::GemmGroup() : args(new GroupedGemmArgs()), n_tiles(0) { args->n_problems = 0; }
+GemmGroup::~GemmGroup() { delete args; }
+
+static GemmProblem* next_problem(GemmGroup* grp, int M, int N) {
+    GemmProblem* g = &grp->args->p[grp->args->n_problems++];
+    memset(g, 0, sizeof(*g));
+    g->tiles_n = (N + kBN - 1) / kBN;
+    g->tile_begin = grp->n_tiles;
+    grp->n_tiles += g->tiles_n * ((M + kBM - 1) / kBM);
+    return g;
 }
 
-// dX[rows, in] = (dZ[rows, out] W[out, in]) * act'(Xact[rows, in])
-void linear_backward_x(const float* dZ, const float* W, const float* Xact, float* dX, int rows, int in, int out,
-                       int act, cudaStream_t s) {
-    GemmArgs g{};
-    g.A = dZ; g.lda = out; g.B = W; g.ldb = in; g.C = dX; g.ldc = in;
-    g.M = rows; g.N = in; g.K = out;
-    g.aux = Xact; g.ldaux = in; g.act = act;
-    launch_gemm<true, false, EPI_BWD_X>(g, vec4_ok(dZ, out, out), vec4_ok(W, in, in), s);
+void GemmGroup::add_forward(const float* X, int ldx, const int64_t* idx, const float* W, const float* b, float* Y,
+                            int rows, int in, int out, int act) {
+    GemmProblem* g = next_problem(this, rows, out);
+    g->A = X; g->lda = ldx; g->B = W; g->ldb = in; g->C = Y; g->ldc = out;
+    g->M = rows; g->N = out; g->K = in;
+    g->idxA = idx; g->bias = b; g->act = act;
+    g->flavour = EPI_FWD * 4 + (vec4_ok(X, ldx, in) ? 2 : 0) + (vec4_ok(W, in, in) ? 1 : 0);
 }
 
-// dW[out, in] = dZ[rows, out]^T X[idx][rows, in] ; db[out] = column sums of dZ
-void linear_backward_w(const float* dZ, const float* X, int ldx, const int64_t* idx, const int32_t* cursor,
-                       int cursor_stride, float* dW, float* db, int rows, int in, int out, cudaStream_t s) {
-    GemmArgs g{};
-    g.A = dZ; g.lda = out; g.B = X; g.ldb = ldx; g.C = dW; g.ldc = in;
-    g.M = out; g.N = in; g.K = rows;
-    g.idxA = nullptr; g.idxB = idx; g.cursor = cursor; g.cursor_stride = cursor_stride;
-    g.dbias = db;
-    launch_gemm<false, false, EPI_BWD_W>(g, vec4_ok(dZ, out, out), vec4_ok(X, ldx, in), s);
+void GemmGroup::add_backward_x(const float* dZ, const float* W, const float* Xact, float* dX, int rows, int in,
+                               int out, int act) {
+    GemmProblem* g = next_problem(this, rows, in);
+    g->A = dZ; g->lda = out; g->B = W; g->ldb = in; g->C = dX; g->ldc = in;
+    g->M = rows; g->N = in; g->K = out;
+    g->aux = Xact; g->ldaux = in; g->act = act;
+    g->flavour = EPI_BWD_X * 4 + (vec4_ok(dZ, out, out) ? 2 : 0) + (vec4_ok(W, in, in) ? 1 : 0);
+}
+
+int backward_w_tiles(int in, int out) { return ((in + kBN - 1) / kBN) * ((out + kBM - 1) / kBM); }
+
+int GemmGroup::add_backward_w(const float* dZ, const float* X, int ldx, const int64_t* idx, float* dW, float* db,
+                              int rows, int in, int out, double* sq_out) {
+    GemmProblem* g = next_problem(this, out, in);
+    g->A = dZ; g->lda = out; g->B = X; g->ldb = ldx; g->C = dW; g->ldc = in;
+    g->M = out; g->N = in; g->K = rows;
+    g->idxB = idx; g->dbias = db; g->sq_out = sq_out;
+    g->flavour = EPI_BWD_W * 4 + (vec4_ok(dZ, out, out) ? 2 : 0) + (vec4_ok(X, ldx, in) ? 1 : 0);
+    return backward_w_tiles(in, out);
+}
+
+int GemmGroup::launch(const int32_t* cursor, int cursor_stride, cudaStream_t s) {
+    if (n_tiles == 0) return 0;
+    args->cursor = cursor;
+    args->cursor_stride = cursor_stride;
+    grouped_gemm_kernel<<<n_tiles, kThreads, kGemmSmemBytes, s>>>(*args);
+    PPOAF_CHECK_LAUNCH("grouped_gemm_kernel");
+    return 0;
 }
 
 __global__ void softmax_rows_kernel(float* __restrict__ y, int rows, int n) {
@@ -129,9 +137,10 @@ extern "C" int ppoaf_mlp_forward(const ppoaf_mlp_desc* net, const float* params,
     for (int l = 0; l < net->n_layers; ++l) {
         const bool last = l + 1 == net->n_layers;
         float* out = last ? y : buf[l & 1];
-        linear_forward(in, net->dims[l], in_idx, nullptr, 0, params + off[2 * l], params + off[2 * l + 1], out, n_rows,
-                       net->dims[l], net->dims[l + 1], last ? PPOAF_ACT_IDENTITY : net->activation, s);
-        PPOAF_CHECK_LAUNCH("ppoaf_mlp_forward(layer)");
+        GemmGroup grp;
+        grp.add_forward(in, net->dims[l], in_idx, params + off[2 * l], params + off[2 * l + 1], out, n_rows,
+                        net->dims[l], net->dims[l + 1], last ? PPOAF_ACT_IDENTITY : net->activation);
+        if (grp.launch(nullptr, 0, s)) return 2;
         in = out;
         in_idx = nullptr;
     }

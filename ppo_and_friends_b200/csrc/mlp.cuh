@@ -1,8 +1,20 @@
-// fp32 tiled GEMM core for the actor/critic MLP layers at reference minibatch sizes (B = 128..512,
-// hidden 64..512), where a layer is far too small to be a dense tensor-core contraction (SURVEY.md
-// §8d): FFMA register tiles fed from double-buffered shared memory, 128-bit global loads, fused
-// bias / activation / activation-derivative epilogues and a fused row gather on the operand that
-// is indexed by sample (the minibatch permutation), so the gathered minibatch never exists in HBM.
+// fp32 grouped-GEMM core for the actor/critic MLP layers at reference minibatch sizes (B = 128..512,
+// hidden 64..512).  One layer of one network is ~30-50 MFLOP: far too small to be a dense
+// tensor-core contraction, and a minibatch step is a chain of ~10 dependent phases,
+// so the design goal is latency per phase and launches per step, not peak FLOP/s:
+//
+//   * GROUPED launches: one launch computes every GEMM of a phase (actor and critic forward layer l;
+//     or dW and dX of layer l for both networks), so a step is 8 GEMM launches instead of 22 and
+//     each launch fills the 148 SMs with 32x64 output tiles;
+//   * 256 threads per CTA = 8 warps, each warp a K-group owning 1/8 of every K chunk with an 8x8
+//     register microtile (intra-CTA split-K; partial tiles are summed through shared memory).
+//     8x8 is the smallest microtile for which the shared-memory pipe (4 cycles per LDS.128) does
+//     not cap the FFMA pipe: 16 LDS.128 per 256 FFMA per warp;
+//   * operands stream through a 4-stage cp.async ring with BK = 64, in their GLOBAL orientation
+//     (so 16-byte cp.async serves all three GEMM flavours, with zero-fill for ragged edges);
+//   * fused epilogues (bias + activation; activation derivative; bias gradient + per-tile sum of
+//     squares for the gradient-norm clip) and a fused row gather on the operand indexed by sample,
+//     so the gathered minibatch never exists in HBM.
 //
 //   forward      Y[m,n]  = act(sum_k X[idx[m],k] W[n,k] + b[n])        FeedForwardNetwork.forward
 //   backward-x   dX[m,k] = (sum_n dZ[m,n] W[n,k]) * act'(Xact[m,k])    autograd of the same
@@ -31,149 +43,251 @@ __device__ __forceinline__ float act_bwd_from_out(float y, int act) {
 }
 
 enum { EPI_FWD = 0, EPI_BWD_X = 1, EPI_BWD_W = 2 };
+constexpr int kMaxGroup = 4;
 
-struct GemmArgs {
-    const float* A; int lda;        // A(m, r): A_RED_CONTIG ? A[rowA(m)*lda + r] : A[rowA(r)*lda + m]
-    const float* B; int ldb;        // B(r, n): B_RED_CONTIG ? B[n*ldb + r]       : B[rowB(r)*ldb + n]
-    float* C; int ldc;              // C[m*ldc + n]
-    int M, N, K;                    // C is M x N, reduction length K
+struct GemmProblem {
+    const float* A; const float* B; float* C;
+    const float* bias;              // EPI_FWD: bias[n]
+    const float* aux;               // EPI_BWD_X: activation output of the layer below, aux[m*ldaux + n]
+    float* dbias;                   // EPI_BWD_W: dbias[m] = sum_r A(m, r)
+    double* sq_out;                 // EPI_BWD_W: sq_out[tile] = sum of squares of this tile of dW (+ db), or null
     const int64_t* idxA;            // optional row indirection on A's row index
     const int64_t* idxB;            // optional row indirection on B's row index
-    const int32_t* cursor;          // optional device scalar: idx tables start at (*cursor) * cursor_stride
-    int cursor_stride;              //   (the minibatch cursor, so one captured graph serves every minibatch)
-    const float* bias;              // EPI_FWD: bias[n]
-    const float* aux; int ldaux;    // EPI_BWD_X: activation output of the layer below, aux[m*ldaux + n]
-    float* dbias;                   // EPI_BWD_W: dbias[m] = sum_r A(m, r)
+    int lda, ldb, ldc, ldaux;       // A(m,r): A_RC ? A[row(m)*lda + r] : A[row(r)*lda + m];  B likewise with n
+    int M, N, K;                    // C is M x N, reduction length K
     int act;
+    int flavour;                    // epi * 4 + (VA == 4) * 2 + (VB == 4)
+    int tiles_n;                    // number of tiles along N
+    int tile_begin;                 // first linear tile id of this problem inside the launch
+};
+struct GroupedGemmArgs {
+    int n_problems;
+    int cursor_stride;              // idx tables start at (*cursor) * cursor_stride (the minibatch cursor, so
+    const int32_t* cursor;          //   one captured graph serves every minibatch); cursor may be null
+    GemmProblem p[kMaxGroup];
 };
 
-// Stage one operand tile (OUT x BK) from global memory into registers.  A "slot" is V consecutive
-// floats along the operand's contiguous global dimension: the reduction dim when RED_CONTIG,
-// otherwise the output dim.  Out-of-range elements are zero.
-template <int OUT, int BK, int NT, bool RED_CONTIG, int V>
-__device__ __forceinline__ void stage_tile(float (&regs)[(OUT * BK / V + NT - 1) / NT][V], const float* __restrict__ P,
-                                           int ld, const int64_t* __restrict__ idx, int out0, int out_ext, int r0,
+constexpr int kBM = 32, kBN = 64, kBK = 64, kStages = 4, kThreads = 512, kGroups = 16;
+constexpr int kLdRC = kBK + 4;         // [out][BK+4]: 68 = 4*17, consecutive rows land on distinct 16-byte bank groups
+constexpr int kLdOCA = kBM + 4;        // A output-contiguous: [BK][32+4]
+constexpr int kLdOCB = kBN + 4;        // B output-contiguous: [BK][64+4]
+constexpr int kAFloats = (kBM * kLdRC > kBK * kLdOCA ? kBM * kLdRC : kBK * kLdOCA);
+constexpr int kBFloats = (kBN * kLdRC > kBK * kLdOCB ? kBN * kLdRC : kBK * kLdOCB);
+constexpr int kStageFloats = kAFloats + kBFloats;
+constexpr int kRedLd = kBN + 1;
+constexpr int kRedFloats = kGroups * kBM * kRedLd + kGroups * kBM;
+constexpr size_t kGemmSmemBytes =
+    sizeof(float) * size_t(kStages * kStageFloats > kRedFloats ? kStages * kStageFloats : kRedFloats);
+
+__device__ __forceinline__ void cp_async_16(float* smem_dst, const float* gmem_src, bool valid) {
+    const unsigned s = static_cast<unsigned>(__cvta_generic_to_shared(smem_dst));
+    const int bytes = valid ? 16 : 0;   // src-size 0: the 16 destination bytes are zero-filled
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(s), "l"(gmem_src), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void cp_async_4(float* smem_dst, const float* gmem_src, bool valid) {
+    const unsigned s = static_cast<unsigned>(__cvta_generic_to_shared(smem_dst));
+    const int bytes = valid ? 4 : 0;
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 4, %2;" ::"r"(s), "l"(gmem_src), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+
+// Issue the cp.async's of one K chunk of one operand (OUT x 64 floats) into its shared tile.
+//   RC (reduction-contiguous in global): tile[out][r], element P[row(out0+o)*ld + r0 + r]
+//   OC (output-contiguous in global):    tile[r][out], element P[row(r0+r)*ld + out0 + o]
+template <int OUT, bool RC, int V>
+__device__ __forceinline__ void load_chunk(float* tile, const float* __restrict__ P, int ld,
+                                           const int64_t* __restrict__ idx, int out0, int out_ext, int r0,
                                            int red_ext, int tid) {
-    constexpr int SLOTS = (OUT * BK / V + NT - 1) / NT;
-#pragma unroll
+    constexpr int LD_OC = OUT + 4;
+    constexpr int SLOTS = OUT * kBK / V / kThreads;
+    static_assert(OUT * kBK / V % kThreads == 0, "slot count");
+#pragma unroll     // unrolled on purpose: the (gathered) row-index loads of all slots must be in flight together
     for (int s = 0; s < SLOTS; ++s) {
-        const int slot = tid + s * NT;
-#pragma unroll
-        for (int j = 0; j < V; ++j) regs[s][j] = 0.f;
-        if (slot >= OUT * BK / V) continue;
+        const int slot = tid + s * kThreads;
         int o, r;
-        if constexpr (RED_CONTIG) { o = slot / (BK / V); r = (slot % (BK / V)) * V; }
-        else                      { r = slot / (OUT / V); o = (slot % (OUT / V)) * V; }
+        if constexpr (RC) { o = slot / (kBK / V); r = (slot % (kBK / V)) * V; }
+        else              { r = slot / (OUT / V); o = (slot % (OUT / V)) * V; }
         const int go = out0 + o, gr = r0 + r;
-        if (go >= out_ext || gr >= red_ext) continue;
-        const int row_sel = RED_CONTIG ? go : gr;
-        const int col_sel = RED_CONTIG ? gr : go;
-        const int64_t row = idx ? idx[row_sel] : int64_t(row_sel);
-        const float* p = P + row * ld + col_sel;
-        if constexpr (V == 4) {
-            const float4 t = *reinterpret_cast<const float4*>(p);
-            regs[s][0] = t.x; regs[s][1] = t.y; regs[s][2] = t.z; regs[s][3] = t.w;
-        } else {
-            regs[s][0] = *p;
+        const bool ok = go < out_ext && gr < red_ext;
+        const float* src = P;
+        if (ok) {
+            const int row_sel = RC ? go : gr, col_sel = RC ? gr : go;
+            const int64_t row = idx ? idx[row_sel] : int64_t(row_sel);
+            src = P + row * ld + col_sel;
+        }
+        float* dst = RC ? tile + o * kLdRC + r : tile + r * LD_OC + o;
+        if constexpr (V == 4) cp_async_16(dst, src, ok); else cp_async_4(dst, src, ok);
+    }
+}
+
+// Position of microtile element i (0..7) of lane-coordinate t inside an operand tile of OUT rows:
+//   RC: t + (OUT/8) * i             (consecutive lanes -> consecutive rows: conflict-free LDS.128 along k)
+//   OC: two runs of 4 contiguous    (consecutive lanes -> one contiguous 16-byte-per-lane span)
+template <int OUT, bool RC>
+__device__ __forceinline__ int frag_pos(int t, int i) {
+    if constexpr (RC) return t + (OUT / 8) * i;
+    else return (i < 4) ? 4 * t + i : OUT / 2 + 4 * t + (i - 4);
+}
+
+// f[i][q] = operand(out_i, kk + q), 8 outputs x 4 k's
+template <int OUT, bool RC>
+__device__ __forceinline__ void load_frag(float (&f)[8][4], const float* tile, int t, int kk) {
+    if constexpr (RC) {
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+            const float4 v = *reinterpret_cast<const float4*>(tile + (t + (OUT / 8) * i) * kLdRC + kk);
+            f[i][0] = v.x; f[i][1] = v.y; f[i][2] = v.z; f[i][3] = v.w;
+        }
+    } else {
+        constexpr int LD_OC = OUT + 4;
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+            const float4 lo = *reinterpret_cast<const float4*>(tile + (kk + q) * LD_OC + 4 * t);
+            const float4 hi = *reinterpret_cast<const float4*>(tile + (kk + q) * LD_OC + OUT / 2 + 4 * t);
+            f[0][q] = lo.x; f[1][q] = lo.y; f[2][q] = lo.z; f[3][q] = lo.w;
+            f[4][q] = hi.x; f[5][q] = hi.y; f[6][q] = hi.z; f[7][q] = hi.w;
         }
     }
 }
 
-// Commit staged registers into the k-major shared tile S[BK][OUT + 4].
-template <int OUT, int BK, int NT, bool RED_CONTIG, int V>
-__device__ __forceinline__ void commit_tile(const float (&regs)[(OUT * BK / V + NT - 1) / NT][V],
-                                            float (*S)[OUT + 4], int tid) {
-    constexpr int SLOTS = (OUT * BK / V + NT - 1) / NT;
-#pragma unroll
-    for (int s = 0; s < SLOTS; ++s) {
-        const int slot = tid + s * NT;
-        if (slot >= OUT * BK / V) continue;
-        if constexpr (RED_CONTIG) {
-            const int o = slot / (BK / V), r = (slot % (BK / V)) * V;
-#pragma unroll
-            for (int j = 0; j < V; ++j) S[r + j][o] = regs[s][j];
-        } else {
-            const int r = slot / (OUT / V), o = (slot % (OUT / V)) * V;
-            if constexpr (V == 4) {
-                *reinterpret_cast<float4*>(&S[r][o]) = make_float4(regs[s][0], regs[s][1], regs[s][2], regs[s][3]);
-            } else {
-                S[r][o] = regs[s][0];
-            }
-        }
-    }
-}
-
-template <int BM, int BN, int BK, bool A_RED_CONTIG, bool B_RED_CONTIG, int VA, int VB, int EPI>
-__global__ void __launch_bounds__((BM / 4) * (BN / 4)) gemm_tile_kernel(const GemmArgs g) {
-    constexpr int NT = (BM / 4) * (BN / 4);
-    __shared__ __align__(16) float As[2][BK][BM + 4];
-    __shared__ __align__(16) float Bs[2][BK][BN + 4];
-
+template <bool A_RC, bool B_RC, int VA, int VB, int EPI>
+__device__ __forceinline__ void gemm_tile(const GemmProblem& g, int tile, int64_t idx_off, float* smem) {
     const int tid = threadIdx.x;
-    const int tx = tid % (BN / 4), ty = tid / (BN / 4);
-    const int m0 = blockIdx.y * BM, n0 = blockIdx.x * BN;
-
-    const int64_t idx_off = g.cursor ? int64_t(*g.cursor) * g.cursor_stride : 0;
+    const int grp = tid >> 5, lane = tid & 31;
+    const int tx = lane & 7, ty = lane >> 3;                  // 8 column-lanes x 4 row-lanes per warp
+    const int m0 = (tile / g.tiles_n) * kBM, n0 = (tile % g.tiles_n) * kBN;
     const int64_t* idxA = g.idxA ? g.idxA + idx_off : nullptr;
     const int64_t* idxB = g.idxB ? g.idxB + idx_off : nullptr;
 
-    float ra[(BM * BK / VA + NT - 1) / NT][VA];
-    float rb[(BN * BK / VB + NT - 1) / NT][VB];
-
-    float acc[4][4];
-#pragma unroll
-    for (int i = 0; i < 4; ++i)
-#pragma unroll
-        for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
-    float bsum[4] = {0.f, 0.f, 0.f, 0.f};
-
-    const int n_tiles = (g.K + BK - 1) / BK;
-    stage_tile<BM, BK, NT, A_RED_CONTIG, VA>(ra, g.A, g.lda, idxA, m0, g.M, 0, g.K, tid);
-    stage_tile<BN, BK, NT, B_RED_CONTIG, VB>(rb, g.B, g.ldb, idxB, n0, g.N, 0, g.K, tid);
-    commit_tile<BM, BK, NT, A_RED_CONTIG, VA>(ra, As[0], tid);
-    commit_tile<BN, BK, NT, B_RED_CONTIG, VB>(rb, Bs[0], tid);
-    __syncthreads();
-    for (int t = 0; t < n_tiles; ++t) {
-        const int buf = t & 1;
-        if (t + 1 < n_tiles) {
-            stage_tile<BM, BK, NT, A_RED_CONTIG, VA>(ra, g.A, g.lda, idxA, m0, g.M, (t + 1) * BK, g.K, tid);
-            stage_tile<BN, BK, NT, B_RED_CONTIG, VB>(rb, g.B, g.ldb, idxB, n0, g.N, (t + 1) * BK, g.K, tid);
+    const int n_chunks = (g.K + kBK - 1) / kBK;
+    auto issue = [&](int c) {
+        if (c < n_chunks) {
+            float* st = smem + (c % kStages) * kStageFloats;
+            load_chunk<kBM, A_RC, VA>(st, g.A, g.lda, idxA, m0, g.M, c * kBK, g.K, tid);
+            load_chunk<kBN, B_RC, VB>(st + kAFloats, g.B, g.ldb, idxB, n0, g.N, c * kBK, g.K, tid);
         }
+        cp_async_commit();
+    };
+#pragma unroll 1
+    for (int s = 0; s < kStages - 1; ++s) issue(s);
+
+    float acc[8][8];
 #pragma unroll
-        for (int kk = 0; kk < BK; ++kk) {
-            const float4 a = *reinterpret_cast<const float4*>(&As[buf][kk][ty * 4]);
-            const float4 b = *reinterpret_cast<const float4*>(&Bs[buf][kk][tx * 4]);
-            const float av[4] = {a.x, a.y, a.z, a.w}, bv[4] = {b.x, b.y, b.z, b.w};
+    for (int i = 0; i < 8; ++i)
 #pragma unroll
-            for (int i = 0; i < 4; ++i) {
+        for (int j = 0; j < 8; ++j) acc[i][j] = 0.f;
+    float bsum[8];
 #pragma unroll
-                for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(av[i], bv[j], acc[i][j]);
-                if constexpr (EPI == EPI_BWD_W) bsum[i] += av[i];
+    for (int i = 0; i < 8; ++i) bsum[i] = 0.f;
+
+    for (int c = 0; c < n_chunks; ++c) {
+        cp_async_wait<kStages - 2>();
+        __syncthreads();                       // chunk c has landed for everyone; chunk c-1's stage is free
+        issue(c + kStages - 1);
+        const float* a_tile = smem + (c % kStages) * kStageFloats;
+        const float* b_tile = a_tile + kAFloats;
+        const int kbase = grp * (kBK / kGroups);
+#pragma unroll 1   // one 8x8x4 block (16 LDS.128 + 256 FFMA) is the whole hot loop body
+        for (int kb = 0; kb < kBK / kGroups; kb += 4) {
+            float a[8][4], b[8][4];
+            load_frag<kBM, A_RC>(a, a_tile, ty, kbase + kb);
+            load_frag<kBN, B_RC>(b, b_tile, tx, kbase + kb);
+#pragma unroll
+            for (int q = 0; q < 4; ++q)
+#pragma unroll
+                for (int i = 0; i < 8; ++i) {
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) acc[i][j] = fmaf(a[i][q], b[j][q], acc[i][j]);
+                    if constexpr (EPI == EPI_BWD_W) bsum[i] += a[i][q];
+                }
+        }
+    }
+    cp_async_wait<0>();
+    __syncthreads();                           // pipeline memory is reused for the split-K reduction
+
+    float* red = smem;                         // [8 groups][32][65]
+#pragma unroll
+    for (int i = 0; i < 8; ++i)
+#pragma unroll
+        for (int j = 0; j < 8; ++j)
+            red[(grp * kBM + frag_pos<kBM, A_RC>(ty, i)) * kRedLd + frag_pos<kBN, B_RC>(tx, j)] = acc[i][j];
+    float* red_b = smem + kGroups * kBM * kRedLd;    // [8 groups][32]
+    if constexpr (EPI == EPI_BWD_W) {
+        if (tx == 0) {
+#pragma unroll
+            for (int i = 0; i < 8; ++i) red_b[grp * kBM + frag_pos<kBM, A_RC>(ty, i)] = bsum[i];
+        }
+    }
+    __syncthreads();
+
+    // 2048 outputs / 512 threads: thread handles row r, columns c8 .. c8+3
+    constexpr int kColsPerThread = kBM * kBN / kThreads;
+    const int r = tid / (kBN / kColsPerThread), c8 = (tid % (kBN / kColsPerThread)) * kColsPerThread;
+    const int m = m0 + r;
+    float sq = 0.f;
+    if (m < g.M) {
+#pragma unroll 1
+        for (int j = 0; j < kColsPerThread; ++j) {
+            const int n = n0 + c8 + j;
+            if (n >= g.N) continue;
+            float o = 0.f;
+#pragma unroll
+            for (int gq = 0; gq < kGroups; ++gq) o += red[(gq * kBM + r) * kRedLd + c8 + j];
+            if constexpr (EPI == EPI_FWD) o = act_fwd(o + g.bias[n], g.act);
+            if constexpr (EPI == EPI_BWD_X) o *= act_bwd_from_out(g.aux[int64_t(m) * g.ldaux + n], g.act);
+            if constexpr (EPI == EPI_BWD_W) sq = fmaf(o, o, sq);
+            g.C[int64_t(m) * g.ldc + n] = o;
+        }
+        if constexpr (EPI == EPI_BWD_W) {
+            if (n0 == 0 && c8 == 0 && g.dbias) {
+                float s = 0.f;
+#pragma unroll
+                for (int gq = 0; gq < kGroups; ++gq) s += red_b[gq * kBM + r];
+                g.dbias[m] = s;
+                sq = fmaf(s, s, sq);
             }
         }
-        if (t + 1 < n_tiles) {
-            commit_tile<BM, BK, NT, A_RED_CONTIG, VA>(ra, As[buf ^ 1], tid);
-            commit_tile<BN, BK, NT, B_RED_CONTIG, VB>(rb, Bs[buf ^ 1], tid);
-        }
-        __syncthreads();
     }
+    if constexpr (EPI == EPI_BWD_W) {
+        if (g.sq_out) {                        // per-tile sum of squares -> gradient-norm clip without a norm pass
+            __shared__ double s_sq[kThreads / 32];
+            const double w = warp_sum(double(sq));
+            if (lane == 0) s_sq[grp] = w;
+            __syncthreads();
+            if (tid == 0) {
+                double t = 0.0;
+#pragma unroll
+                for (int k = 0; k < kThreads / 32; ++k) t += s_sq[k];
+                g.sq_out[tile] = t;
+            }
+        }
+    }
+}
 
+__global__ void __launch_bounds__(kThreads) grouped_gemm_kernel(const GroupedGemmArgs args) {
+    extern __shared__ __align__(16) float smem[];
+    int p = 0;
 #pragma unroll
-    for (int i = 0; i < 4; ++i) {
-        const int m = m0 + ty * 4 + i;
-        if (m >= g.M) continue;
-        if constexpr (EPI == EPI_BWD_W) {
-            if (blockIdx.x == 0 && tx == 0 && g.dbias) g.dbias[m] = bsum[i];
-        }
-#pragma unroll
-        for (int j = 0; j < 4; ++j) {
-            const int n = n0 + tx * 4 + j;
-            if (n >= g.N) continue;
-            float v = acc[i][j];
-            if constexpr (EPI == EPI_FWD) v = act_fwd(v + g.bias[n], g.act);
-            if constexpr (EPI == EPI_BWD_X) v *= act_bwd_from_out(g.aux[int64_t(m) * g.ldaux + n], g.act);
-            g.C[int64_t(m) * g.ldc + n] = v;
-        }
+    for (int i = 1; i < kMaxGroup; ++i)
+        if (i < args.n_problems && int(blockIdx.x) >= args.p[i].tile_begin) p = i;
+    const GemmProblem& g = args.p[p];
+    const int tile = int(blockIdx.x) - g.tile_begin;
+    const int64_t idx_off = args.cursor ? int64_t(*args.cursor) * args.cursor_stride : 0;
+    switch (g.flavour) {
+        case EPI_FWD * 4 + 3: gemm_tile<true, true, 4, 4, EPI_FWD>(g, tile, idx_off, smem); break;
+        case EPI_FWD * 4 + 2: gemm_tile<true, true, 4, 1, EPI_FWD>(g, tile, idx_off, smem); break;
+        case EPI_FWD * 4 + 1: gemm_tile<true, true, 1, 4, EPI_FWD>(g, tile, idx_off, smem); break;
+        case EPI_FWD * 4 + 0: gemm_tile<true, true, 1, 1, EPI_FWD>(g, tile, idx_off, smem); break;
+        case EPI_BWD_X * 4 + 3: gemm_tile<true, false, 4, 4, EPI_BWD_X>(g, tile, idx_off, smem); break;
+        case EPI_BWD_X * 4 + 2: gemm_tile<true, false, 4, 1, EPI_BWD_X>(g, tile, idx_off, smem); break;
+        case EPI_BWD_X * 4 + 1: gemm_tile<true, false, 1, 4, EPI_BWD_X>(g, tile, idx_off, smem); break;
+        case EPI_BWD_X * 4 + 0: gemm_tile<true, false, 1, 1, EPI_BWD_X>(g, tile, idx_off, smem); break;
+        case EPI_BWD_W * 4 + 3: gemm_tile<false, false, 4, 4, EPI_BWD_W>(g, tile, idx_off, smem); break;
+        case EPI_BWD_W * 4 + 2: gemm_tile<false, false, 4, 1, EPI_BWD_W>(g, tile, idx_off, smem); break;
+        case EPI_BWD_W * 4 + 1: gemm_tile<false, false, 1, 4, EPI_BWD_W>(g, tile, idx_off, smem); break;
+        default: gemm_tile<false, false, 1, 1, EPI_BWD_W>(g, tile, idx_off, smem); break;
     }
 }
 

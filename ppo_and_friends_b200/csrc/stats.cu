@@ -105,22 +105,24 @@ __global__ void moments_partial_kernel(const float4* __restrict__ x, int64_t row
     }
 }
 
-// One warp per TRUE column: lanes stride over (CTA, fold) partials, then a shuffle tree merge.
-__global__ void moments_finalize_kernel(const double* __restrict__ partial, int n_blocks, int width, int dim,
-                                        int fold, const float* __restrict__ tail_rows, int64_t tail,
-                                        double* __restrict__ triple_out) {
-    const int lane = threadIdx.x & 31;
-    const int col = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-    if (col >= dim) return;
+// One CTA per TRUE column: threads stride over the (CTA, fold) partials, then a shuffle tree merge inside
+// each warp and a fixed-order merge of the warps (Chan), so the result is deterministic.
+constexpr int kFinThreads = 128;
+__global__ void __launch_bounds__(kFinThreads)
+moments_finalize_kernel(const double* __restrict__ partial, int n_blocks, int width, int dim, int fold,
+                        const float* __restrict__ tail_rows, int64_t tail, double* __restrict__ triple_out) {
+    __shared__ Moments s_w[kFinThreads / 32];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int col = blockIdx.x;
     Moments acc{0.0, 0.0, 0.0};
     const int items = n_blocks * fold;
-    for (int it = lane; it < items; it += 32) {
+    for (int it = threadIdx.x; it < items; it += kFinThreads) {
         const int b = it / fold, j = it - b * fold;
         const double* p = partial + (size_t(b) * width + size_t(j) * dim + col) * 3;
         Moments m{p[0], p[1], p[2]};
         acc = merge_moments(acc, m);
     }
-    for (int64_t t = lane; t < tail; t += 32) {
+    for (int64_t t = threadIdx.x; t < tail; t += kFinThreads) {
         Moments m{1.0, double(tail_rows[t * dim + col]), 0.0};
         acc = merge_moments(acc, m);
     }
@@ -130,10 +132,14 @@ __global__ void moments_finalize_kernel(const double* __restrict__ partial, int 
         // merge in a fixed (lower lane first) order so both partners compute the same bits
         acc = (lane & o) ? merge_moments(other, acc) : merge_moments(acc, other);
     }
-    if (lane == 0) {
-        triple_out[col] = acc.mean;
-        triple_out[dim + col] = acc.m2;
-        if (col == 0) triple_out[2 * dim] = acc.n;
+    if (lane == 0) s_w[warp] = acc;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        Moments t = s_w[0];
+        for (int w = 1; w < kFinThreads / 32; ++w) t = merge_moments(t, s_w[w]);
+        triple_out[col] = t.mean;
+        triple_out[dim + col] = t.m2;
+        if (col == 0) triple_out[2 * dim] = t.n;
     }
 }
 
@@ -338,7 +344,7 @@ extern "C" int ppoaf_batch_moments(const float* x, int64_t n_rows, int32_t dim, 
     const size_t smem = size_t(kStatRowsPerBlock) * f.width * 2 * sizeof(double);
     moments_partial_kernel<<<f.grid, block, smem, s>>>(reinterpret_cast<const float4*>(x), f.rows, f.vec, partial);
     PPOAF_CHECK_LAUNCH("ppoaf_batch_moments(partial)");
-    moments_finalize_kernel<<<fin_blocks, warps_per_block * 32, 0, s>>>(
+    moments_finalize_kernel<<<dim, kFinThreads, 0, s>>>(
         partial, f.grid, f.width, dim, f.fold, x + f.rows * f.fold * int64_t(dim), f.tail, triple_out);
     PPOAF_CHECK_LAUNCH("ppoaf_batch_moments(finalize)");
     return 0;

@@ -70,8 +70,17 @@ struct StepScratch {
     float* loss_partials;
     unsigned int* loss_ticket;
     void* optim_ws;
+    double* sq_actor;   // per-tile sums of squares of the actor's gradient (+1 slot for log_std)
+    double* sq_critic;
+    int n_sq_actor, n_sq_critic;
     size_t total;
 };
+
+static int count_sq_slots(const ppoaf_mlp_desc* net) {
+    int n = 0;
+    for (int l = 0; l < net->n_layers; ++l) n += backward_w_tiles(net->dims[l], net->dims[l + 1]);
+    return n;
+}
 
 static void carve(const ppoaf_update_cfg* cfg, int max_batch, char* base, StepScratch* out) {
     size_t off = 0;
@@ -83,7 +92,11 @@ static void carve(const ppoaf_update_cfg* cfg, int max_batch, char* base, StepSc
     // control blocks first, at offsets that do not depend on the batch: they hold self-resetting tickets
     // that must stay zero between launches, so no activation buffer may ever alias them
     out->loss_ticket = reinterpret_cast<unsigned int*>(take(256));
-    out->optim_ws = take(optim_workspace_bytes(0));
+    out->optim_ws = take(optim_workspace_bytes());
+    out->n_sq_actor = count_sq_slots(&cfg->actor) + 1;
+    out->n_sq_critic = count_sq_slots(&cfg->critic);
+    out->sq_actor = reinterpret_cast<double*>(take(size_t(out->n_sq_actor) * sizeof(double)));
+    out->sq_critic = reinterpret_cast<double*>(take(size_t(out->n_sq_critic) * sizeof(double)));
     out->loss_partials = reinterpret_cast<float*>(take(loss_workspace_bytes(max_batch, cfg->act_dim)));
     const ppoaf_mlp_desc* nets[2] = {&cfg->actor, &cfg->critic};
     NetScratch* ns[2] = {&out->actor, &out->critic};
@@ -136,7 +149,11 @@ extern "C" int ppoaf_device_info(int* sm, int* cc_major, int* cc_minor) {
 
 extern "C" int ppoaf_runtime_init(void) {
     SideStream* ss;
-    return get_side_stream(&ss);
+    if (get_side_stream(&ss)) return 1;
+    configure_gemm_kernels();
+    cudaError_t e = cudaGetLastError();
+    PPOAF_CHECK_ARG(e == cudaSuccess, "ppoaf_runtime_init: %s", cudaGetErrorString(e));
+    return 0;
 }
 
 extern "C" size_t ppoaf_update_workspace_bytes(const ppoaf_update_cfg* cfg, int32_t max_batch) {
@@ -144,35 +161,6 @@ extern "C" size_t ppoaf_update_workspace_bytes(const ppoaf_update_cfg* cfg, int3
     StepScratch s;
     carve(cfg, max_batch, nullptr, &s);
     return s.total;
-}
-
-static int run_net_forward(const ppoaf_mlp_desc* net, const float* params, const int64_t* off, const float* x,
-                           const ppoaf_update_bufs* b, NetScratch* ns, cudaStream_t s) {
-    for (int l = 0; l < net->n_layers; ++l) {
-        const bool first = l == 0, last = l + 1 == net->n_layers;
-        linear_forward(first ? x : ns->act[l], net->dims[l], first ? b->perm : nullptr, first ? b->mb_cursor : nullptr,
-                       b->batch_size, params + off[2 * l], params + off[2 * l + 1], ns->act[l + 1], b->batch,
-                       net->dims[l], net->dims[l + 1], last ? PPOAF_ACT_IDENTITY : net->activation, s);
-        PPOAF_CHECK_LAUNCH("linear_forward");
-    }
-    return 0;
-}
-
-static int run_net_backward(const ppoaf_mlp_desc* net, const float* params, float* grads, const int64_t* off,
-                            const float* x, const ppoaf_update_bufs* b, NetScratch* ns, cudaStream_t s) {
-    for (int l = net->n_layers - 1; l >= 0; --l) {
-        const bool first = l == 0;
-        linear_backward_w(ns->dz[l + 1], first ? x : ns->act[l], net->dims[l], first ? b->perm : nullptr,
-                          first ? b->mb_cursor : nullptr, b->batch_size, grads + off[2 * l], grads + off[2 * l + 1],
-                          b->batch, net->dims[l], net->dims[l + 1], s);
-        PPOAF_CHECK_LAUNCH("linear_backward_w");
-        if (!first) {
-            linear_backward_x(ns->dz[l + 1], params + off[2 * l], ns->act[l], ns->dz[l], b->batch, net->dims[l],
-                              net->dims[l + 1], net->activation, s);
-            PPOAF_CHECK_LAUNCH("linear_backward_x");
-        }
-    }
-    return 0;
 }
 
 #define PPOAF_CUDA_OK(expr, what)                                                      \
@@ -191,35 +179,43 @@ extern "C" int ppoaf_ppo_minibatch_grads(const ppoaf_update_cfg* cfg, const ppoa
     if (b->batch == 1) return 0;  // the reference skips one-row minibatches (ppo.py:2305)
     PPOAF_CHECK_ARG(b->workspace_bytes >= ppoaf_update_workspace_bytes(cfg, b->batch_size),
                     "ppoaf_ppo_minibatch_grads: workspace too small");
-    PPOAF_CHECK_ARG(reinterpret_cast<uintptr_t>(b->workspace) % 256 == 0, "ppoaf_ppo_minibatch_grads: workspace must be 256-byte aligned");
+    PPOAF_CHECK_ARG(reinterpret_cast<uintptr_t>(b->workspace) % 256 == 0,
+                    "ppoaf_ppo_minibatch_grads: workspace must be 256-byte aligned");
     cudaStream_t s = (cudaStream_t)stream;
-    SideStream* ss;
-    if (get_side_stream(&ss)) return 1;
 
     StepScratch sc;
     carve(cfg, b->batch_size, reinterpret_cast<char*>(b->workspace), &sc);  // layout fixed by the nominal B
     const bool gaussian = cfg->head == PPOAF_HEAD_GAUSSIAN_TANH;
-    int64_t off_a[2 * PPOAF_MAX_LAYERS + 1], off_c[2 * PPOAF_MAX_LAYERS + 1];
-    const int64_t n_actor = param_layout(&cfg->actor, gaussian ? cfg->act_dim : 0, off_a);
-    param_layout(&cfg->critic, 0, off_c);
-    const float* pa = b->params;
-    const float* pc = b->params + n_actor;
-    float* ga = b->grads;
-    float* gc = b->grads + n_actor;
-    const int La = cfg->actor.n_layers, Lc = cfg->critic.n_layers;
+    int64_t off[2][2 * PPOAF_MAX_LAYERS + 1];
+    const int64_t n_actor = param_layout(&cfg->actor, gaussian ? cfg->act_dim : 0, off[0]);
+    param_layout(&cfg->critic, 0, off[1]);
+    const ppoaf_mlp_desc* net[2] = {&cfg->actor, &cfg->critic};
+    const float* par[2] = {b->params, b->params + n_actor};
+    float* grd[2] = {b->grads, b->grads + n_actor};
+    const float* x0[2] = {b->obs, b->critic_obs};
+    NetScratch* ns[2] = {&sc.actor, &sc.critic};
+    const int L[2] = {cfg->actor.n_layers, cfg->critic.n_layers};
+    const int Lmax = L[0] > L[1] ? L[0] : L[1];
+    const int rows = b->batch;
 
-    // forward: actor on `s`, critic on the side stream
-    PPOAF_CUDA_OK(cudaEventRecord(ss->fork, s), "event record");
-    PPOAF_CUDA_OK(cudaStreamWaitEvent(ss->stream, ss->fork, 0), "stream wait");
-    if (run_net_forward(&cfg->actor, pa, off_a, b->obs, b, &sc.actor, s)) return 2;
-    if (run_net_forward(&cfg->critic, pc, off_c, b->critic_obs, b, &sc.critic, ss->stream)) return 2;
-    PPOAF_CUDA_OK(cudaEventRecord(ss->join_fwd, ss->stream), "event record");
-    PPOAF_CUDA_OK(cudaStreamWaitEvent(s, ss->join_fwd, 0), "stream wait");
+    // ---- forward: layer l of both networks in one grouped launch ----
+    for (int l = 0; l < Lmax; ++l) {
+        GemmGroup grp;
+        for (int k = 0; k < 2; ++k) {
+            if (l >= L[k]) continue;
+            const bool first = l == 0, last = l + 1 == L[k];
+            grp.add_forward(first ? x0[k] : ns[k]->act[l], net[k]->dims[l], first ? b->perm : nullptr,
+                            par[k] + off[k][2 * l], par[k] + off[k][2 * l + 1], ns[k]->act[l + 1], rows,
+                            net[k]->dims[l], net[k]->dims[l + 1], last ? PPOAF_ACT_IDENTITY : net[k]->activation);
+        }
+        if (grp.launch(b->mb_cursor, b->batch_size, s)) return 2;
+    }
 
+    // ---- fused loss forward/backward ----
     LossArgs a{};
-    a.actor_out = sc.actor.act[La];
-    a.critic_out = sc.critic.act[Lc];
-    a.log_std = gaussian ? pa + off_a[2 * La] : nullptr;
+    a.actor_out = sc.actor.act[L[0]];
+    a.critic_out = sc.critic.act[L[1]];
+    a.log_std = gaussian ? par[0] + off[0][2 * L[0]] : nullptr;
     a.raw_actions = b->raw_actions;
     a.advantages = b->advantages;
     a.log_probs = b->log_probs;
@@ -228,19 +224,20 @@ extern "C" int ppoaf_ppo_minibatch_grads(const ppoaf_update_cfg* cfg, const ppoa
     a.perm = b->perm;
     a.cursor = b->mb_cursor;
     a.batch_size = b->batch_size;
-    a.batch = b->batch;
+    a.batch = rows;
     a.mb_adv_stats = b->mb_adv_stats;
     a.mb_val_stats = b->mb_val_stats;
     a.hparams = b->hparams;
     a.epoch_stats = b->epoch_stats;
-    a.d_actor_out = sc.actor.dz[La];
-    a.d_critic_out = sc.critic.dz[Lc];
-    a.d_log_std = gaussian ? ga + off_a[2 * La] : nullptr;
+    a.d_actor_out = sc.actor.dz[L[0]];
+    a.d_critic_out = sc.critic.dz[L[1]];
+    a.d_log_std = gaussian ? grd[0] + off[0][2 * L[0]] : nullptr;
+    a.sq_log_std = sc.sq_actor + (sc.n_sq_actor - 1);
     a.partials = sc.loss_partials;
     a.ticket = sc.loss_ticket;
     a.head = cfg->head;
     a.act_dim = cfg->act_dim;
-    a.pred_dim = cfg->actor.dims[La];
+    a.pred_dim = cfg->actor.dims[L[0]];
     a.use_huber = cfg->use_huber;
     a.normalize_adv = cfg->normalize_adv;
     a.normalize_values = cfg->normalize_values;
@@ -248,13 +245,25 @@ extern "C" int ppoaf_ppo_minibatch_grads(const ppoaf_update_cfg* cfg, const ppoa
     a.min_std = cfg->min_std;
     if (launch_ppo_loss(a, s)) return 2;
 
-    // backward: actor on `s`, critic on the side stream
-    PPOAF_CUDA_OK(cudaEventRecord(ss->fork_bwd, s), "event record");
-    PPOAF_CUDA_OK(cudaStreamWaitEvent(ss->stream, ss->fork_bwd, 0), "stream wait");
-    if (run_net_backward(&cfg->actor, pa, ga, off_a, b->obs, b, &sc.actor, s)) return 2;
-    if (run_net_backward(&cfg->critic, pc, gc, off_c, b->critic_obs, b, &sc.critic, ss->stream)) return 2;
-    PPOAF_CUDA_OK(cudaEventRecord(ss->join_bwd, ss->stream), "event record");
-    PPOAF_CUDA_OK(cudaStreamWaitEvent(s, ss->join_bwd, 0), "stream wait");
+    // ---- backward: dW/db and dX of one layer of both networks per grouped launch, top layer first ----
+    double* sq[2] = {sc.sq_actor, sc.sq_critic};
+    int sq_used[2] = {0, 0};
+    for (int k_top = 0; k_top < Lmax; ++k_top) {
+        GemmGroup grp;
+        for (int k = 0; k < 2; ++k) {
+            const int l = L[k] - 1 - k_top;
+            if (l < 0) continue;
+            const bool first = l == 0;
+            sq_used[k] += grp.add_backward_w(ns[k]->dz[l + 1], first ? x0[k] : ns[k]->act[l], net[k]->dims[l],
+                                             first ? b->perm : nullptr, grd[k] + off[k][2 * l],
+                                             grd[k] + off[k][2 * l + 1], rows, net[k]->dims[l], net[k]->dims[l + 1],
+                                             sq[k] + sq_used[k]);
+            if (!first)
+                grp.add_backward_x(ns[k]->dz[l + 1], par[k] + off[k][2 * l], ns[k]->act[l], ns[k]->dz[l], rows,
+                                   net[k]->dims[l], net[k]->dims[l + 1], net[k]->activation);
+        }
+        if (grp.launch(b->mb_cursor, b->batch_size, s)) return 2;
+    }
     return 0;
 }
 
@@ -268,6 +277,10 @@ extern "C" int ppoaf_ppo_minibatch_apply(const ppoaf_update_cfg* cfg, const ppoa
     const bool gaussian = cfg->head == PPOAF_HEAD_GAUSSIAN_TANH;
     const int64_t n_actor = param_layout(&cfg->actor, gaussian ? cfg->act_dim : 0, nullptr);
     const int64_t n_critic = param_layout(&cfg->critic, 0, nullptr);
+    // Single rank: the backward-w epilogues already left the per-tile sums of squares.  R > 1: the caller has
+    // all-reduced `grads` in between, so the norm must be taken again over the reduced buffer.
+    const bool fused_norm = cfg->world_size <= 1;
     return launch_clip_adam(b->params, b->grads, b->adam_m, b->adam_v, b->adam_step, b->mb_cursor, b->hparams, n_actor,
-                            n_critic, sc.optim_ws, s);
+                            n_critic, fused_norm ? sc.sq_actor : nullptr, sc.n_sq_actor,
+                            fused_norm ? sc.sq_critic : nullptr, sc.n_sq_critic, sc.optim_ws, s);
 }

@@ -62,6 +62,7 @@ class UpdateEngine:
         cfg.normalize_values = int(self.normalize_values)
         cfg.vf_clip_enabled = int(policy.vf_clip is not None)
         cfg.min_std = policy.min_std
+        cfg.world_size = mpi_utils.get_num_procs()
         self.cfg = cfg
         dev = self.device
         self.hparams_host = torch.zeros(HP["COUNT"], dtype=torch.float64, pin_memory=True)
