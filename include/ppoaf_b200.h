@@ -39,8 +39,8 @@ int         ppoaf_abi_version(void);
 const char* ppoaf_last_error(void);
 /* sm count / compute capability of the current device; fails (nonzero) when no CUDA device. */
 int         ppoaf_device_info(int* sm_count, int* cc_major, int* cc_minor);
-/* Creates the per-thread helper stream/events the composite step uses (call once per device
- * before the first stream capture). */
+/* One-time per-device setup (kernel attributes such as > 48 KB dynamic shared memory); call once
+ * before the first stream capture. */
 int         ppoaf_runtime_init(void);
 
 /* ------------------------------------------------------------------------------------------
@@ -191,7 +191,7 @@ int ppoaf_value_stats_sequence(double* state, const double* mb_val_triples /* [n
 
 /* One minibatch, first half: gather -> actor & critic forward (policies/ppo_policy.py:891-952,
  * networks/ppo_networks/feed_forward.py:66-86) -> fused loss forward/backward (ppo.py:2342-2438)
- * -> backward into `grads` (this rank's gradient SUMMED nothing yet: plain local grads).
+ * -> backward into `grads` (this rank's local gradient).
  * Second half (after the caller's all-reduce of `grads` when R > 1): grads *= 1/R
  * (utils/mpi_utils.py:89-111), per-net clip_grad_norm_ and Adam (policies/ppo_policy.py:1032-1055),
  * then advances mb_cursor and adam_step. */

@@ -74,7 +74,7 @@ constexpr int kLdOCB = kBN + 4;        // B output-contiguous: [BK][64+4]
 constexpr int kAFloats = (kBM * kLdRC > kBK * kLdOCA ? kBM * kLdRC : kBK * kLdOCA);
 constexpr int kBFloats = (kBN * kLdRC > kBK * kLdOCB ? kBN * kLdRC : kBK * kLdOCB);
 constexpr int kStageFloats = kAFloats + kBFloats;
-constexpr int kRedLd = kBN + 1;
+constexpr int kRedLd = kBN + 8;       // 72 = 8 (mod 32): the (ty, tx) lanes of a warp hit 32 distinct banks
 constexpr int kRedFloats = kGroups * kBM * kRedLd + kGroups * kBM;
 constexpr size_t kGemmSmemBytes =
     sizeof(float) * size_t(kStages * kStageFloats > kRedFloats ? kStages * kStageFloats : kRedFloats);
@@ -222,26 +222,31 @@ __device__ __forceinline__ void gemm_tile(const GemmProblem& g, int tile, int64_
     }
     __syncthreads();
 
-    // 2048 outputs / 512 threads: thread handles row r, columns c8 .. c8+3
-    constexpr int kColsPerThread = kBM * kBN / kThreads;
-    const int r = tid / (kBN / kColsPerThread), c8 = (tid % (kBN / kColsPerThread)) * kColsPerThread;
+    // 2048 outputs / 512 threads: thread handles row r, columns c4 .. c4+3 (one LDS.128 per K-group)
+    static_assert(kBM * kBN / kThreads == 4, "epilogue mapping assumes 4 outputs per thread");
+    const int r = tid / (kBN / 4), c4 = (tid % (kBN / 4)) * 4;
     const int m = m0 + r;
     float sq = 0.f;
     if (m < g.M) {
-#pragma unroll 1
-        for (int j = 0; j < kColsPerThread; ++j) {
-            const int n = n0 + c8 + j;
-            if (n >= g.N) continue;
-            float o = 0.f;
+        float4 sum = make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll
-            for (int gq = 0; gq < kGroups; ++gq) o += red[(gq * kBM + r) * kRedLd + c8 + j];
+        for (int gq = 0; gq < kGroups; ++gq) {
+            const float4 v = *reinterpret_cast<const float4*>(red + (gq * kBM + r) * kRedLd + c4);
+            sum.x += v.x; sum.y += v.y; sum.z += v.z; sum.w += v.w;
+        }
+        const float o4[4] = {sum.x, sum.y, sum.z, sum.w};
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const int n = n0 + c4 + j;
+            if (n >= g.N) continue;
+            float o = o4[j];
             if constexpr (EPI == EPI_FWD) o = act_fwd(o + g.bias[n], g.act);
             if constexpr (EPI == EPI_BWD_X) o *= act_bwd_from_out(g.aux[int64_t(m) * g.ldaux + n], g.act);
             if constexpr (EPI == EPI_BWD_W) sq = fmaf(o, o, sq);
             g.C[int64_t(m) * g.ldc + n] = o;
         }
         if constexpr (EPI == EPI_BWD_W) {
-            if (n0 == 0 && c8 == 0 && g.dbias) {
+            if (n0 == 0 && c4 == 0 && g.dbias) {
                 float s = 0.f;
 #pragma unroll
                 for (int gq = 0; gq < kGroups; ++gq) s += red_b[gq * kBM + r];

@@ -68,11 +68,11 @@ __device__ __forceinline__ void st_release(int* p, int v) {
     asm volatile("st.release.gpu.global.s32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
 }
 
-constexpr int kScanThreads = 256;
+constexpr int kScanThreads = 128;
 constexpr int kScanItems = 8;
-constexpr int kScanTile = kScanThreads * kScanItems;  // 2048 timesteps per CTA
+constexpr int kScanTile = kScanThreads * kScanItems;  // 1024 timesteps per CTA
 
-__global__ void __launch_bounds__(kScanThreads)
+__global__ void __launch_bounds__(kScanThreads, 8)
 segscan_kernel(const float* __restrict__ rewards, const float* __restrict__ values,
                const uint8_t* __restrict__ seg_flag, const int64_t* __restrict__ seg_off,
                const float* __restrict__ v_boot, const float* __restrict__ r_boot, int32_t n_seg, int64_t n,

@@ -1,12 +1,12 @@
 // One PPO minibatch as a fixed kernel sequence (reference ppo.py:2292-2468 -> policies/ppo_policy.py:
 // 891-952, 1012-1055), plus the library-wide utilities (error string, device info).
 //
-//   grads:  actor forward || critic forward  ->  fused loss fwd/bwd  ->  actor backward || critic backward
-//   apply:  [caller all-reduces `grads` when R > 1]  ->  grad sum-of-squares + step scalars  ->  clip + Adam
+//   grads:  forward layer l of actor AND critic (one grouped launch per l)  ->  fused loss fwd/bwd
+//           ->  dW/db and dX of layer l of both networks (one grouped launch per l, top layer first)
+//   apply:  [caller all-reduces `grads` when R > 1 -> norm pass]  ->  clip + Adam (one launch)
 //
-// The actor and critic chains are independent until the loss and again after it, so they run on two
-// streams joined by events (capturable: the fork/join becomes graph branches).  Every kernel reads
-// the minibatch cursor from device memory, so ONE captured graph serves every full minibatch.
+// 10 launches per minibatch on one stream.  Every kernel reads the minibatch cursor from device
+// memory, so ONE captured graph serves every full minibatch.
 #include <stdarg.h>
 
 #include "internal.h"
@@ -33,31 +33,6 @@ int sm_count() {
     }
     (void)cudaGetLastError();
     return 148;  // B200; only used for sizing queries when no device is visible
-}
-
-struct SideStream {
-    cudaStream_t stream = nullptr;
-    cudaEvent_t fork = nullptr, join_fwd = nullptr, fork_bwd = nullptr, join_bwd = nullptr;
-    int device = -1;
-};
-
-static int get_side_stream(SideStream** out) {
-    static thread_local SideStream ss;
-    int dev = 0;
-    cudaError_t e = cudaGetDevice(&dev);
-    PPOAF_CHECK_ARG(e == cudaSuccess, "no CUDA device: %s", cudaGetErrorString(e));
-    if (ss.stream == nullptr || ss.device != dev) {
-        e = cudaStreamCreateWithFlags(&ss.stream, cudaStreamNonBlocking);
-        PPOAF_CHECK_ARG(e == cudaSuccess, "cudaStreamCreate failed: %s", cudaGetErrorString(e));
-        cudaEvent_t* evs[4] = {&ss.fork, &ss.join_fwd, &ss.fork_bwd, &ss.join_bwd};
-        for (auto ev : evs) {
-            e = cudaEventCreateWithFlags(ev, cudaEventDisableTiming);
-            PPOAF_CHECK_ARG(e == cudaSuccess, "cudaEventCreate failed: %s", cudaGetErrorString(e));
-        }
-        ss.device = dev;
-    }
-    *out = &ss;
-    return 0;
 }
 
 // ---- workspace carving ------------------------------------------------------------------------------
@@ -148,8 +123,9 @@ extern "C" int ppoaf_device_info(int* sm, int* cc_major, int* cc_minor) {
 }
 
 extern "C" int ppoaf_runtime_init(void) {
-    SideStream* ss;
-    if (get_side_stream(&ss)) return 1;
+    int dev = 0;
+    cudaError_t e0 = cudaGetDevice(&dev);
+    PPOAF_CHECK_ARG(e0 == cudaSuccess, "ppoaf_runtime_init: no CUDA device: %s", cudaGetErrorString(e0));
     configure_gemm_kernels();
     cudaError_t e = cudaGetLastError();
     PPOAF_CHECK_ARG(e == cudaSuccess, "ppoaf_runtime_init: %s", cudaGetErrorString(e));

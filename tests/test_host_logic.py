@@ -39,7 +39,7 @@ def test_sizing_queries_without_gpu():
     # W0 b0 W1 b1 W2 b2 W3 b3 log_std, every tensor on a 4-float boundary
     assert offs[0] == 0 and offs[1] == 376 * 256 and all(o % 4 == 0 for o in offs)
     assert total == offs[-1] + 20
-    assert lib.ppoaf_segscan_workspace_bytes(1 << 22) == (1 << 22) // 2048 * 64 + 64
+    assert lib.ppoaf_segscan_workspace_bytes(1 << 22) == (1 << 22) // 1024 * 64 + 64
     cfg = _lib.UpdateCfg()
     cfg.actor, cfg.critic = desc, _lib.MlpDesc.make([376, 256, 256, 256, 1], "tanh")
     cfg.head, cfg.act_dim = _lib.HEAD_GAUSSIAN_TANH, 17
