@@ -52,6 +52,8 @@ class UpdateEngine:
         self.normalize_values = bool(normalize_values)
         self.value_normalizer = value_normalizer
         self.use_graphs = (os.environ.get("PPOAF_NO_GRAPH", "0") != "1") if use_graphs is None else use_graphs
+        # capturing the NCCL all-reduce inside the step graph is opt-in (PPOAF_GRAPH_COLLECTIVE=1)
+        self.capture_collective = os.environ.get("PPOAF_GRAPH_COLLECTIVE", "0") == "1"
         nets = policy.nets
         cfg = _lib.UpdateCfg()
         cfg.actor, cfg.critic = nets.actor.desc, nets.critic.desc
@@ -112,12 +114,19 @@ class UpdateEngine:
         b.batch, b.batch_size = int(rows), self.batch_size
         return b
 
+    def _grads(self, bufs):
+        check(load().ppoaf_ppo_minibatch_grads(C.byref(self.cfg), C.byref(bufs), stream_ptr()),
+              "ppoaf_ppo_minibatch_grads")
+
+    def _apply(self, bufs):
+        check(load().ppoaf_ppo_minibatch_apply(C.byref(self.cfg), C.byref(bufs), stream_ptr()),
+              "ppoaf_ppo_minibatch_apply")
+
     def _step_eager(self, bufs):
-        lib, cfg = load(), self.cfg
-        check(lib.ppoaf_ppo_minibatch_grads(C.byref(cfg), C.byref(bufs), stream_ptr()), "ppoaf_ppo_minibatch_grads")
+        self._grads(bufs)
         if bufs.batch > 1:
             mpi_utils.mpi_avg_gradients(self.policy.nets.flat_grads)
-        check(lib.ppoaf_ppo_minibatch_apply(C.byref(cfg), C.byref(bufs), stream_ptr()), "ppoaf_ppo_minibatch_apply")
+        self._apply(bufs)
 
     def _ensure_epoch_buffers(self, n):
         n_mb = (n + self.batch_size - 1) // self.batch_size
@@ -131,6 +140,13 @@ class UpdateEngine:
             self._graphs.clear()
         return n_mb
 
+    def _capture(self, fn):
+        graph = torch.cuda.CUDAGraph()
+        torch.cuda.synchronize(self.device)
+        with torch.cuda.graph(graph):
+            fn()
+        return graph
+
     def _launch_step(self, ds, rows):
         key = (rows, ds.observations.data_ptr(), ds.critic_observations.data_ptr(), ds.values.data_ptr(),
                ds.advantages.data_ptr())
@@ -142,13 +158,16 @@ class UpdateEngine:
             if len(self._graphs) > 8:
                 self._graphs.clear()
             bufs = self._bufs(ds, rows)
-            graph = torch.cuda.CUDAGraph()
-            torch.cuda.synchronize(self.device)
-            with torch.cuda.graph(graph):
-                self._step_eager(bufs)
-            g = (graph, bufs)
+            if mpi_utils.get_num_procs() == 1 or self.capture_collective:
+                g = (self._capture(lambda: self._step_eager(bufs)), None, bufs)
+            else:
+                # R > 1: two graphs with the NCCL all-reduce of the flat gradient enqueued between them
+                g = (self._capture(lambda: self._grads(bufs)), self._capture(lambda: self._apply(bufs)), bufs)
             self._graphs[key] = g
         g[0].replay()
+        if g[1] is not None:
+            mpi_utils.mpi_avg_gradients(self.policy.nets.flat_grads)
+            g[1].replay()
 
     # -- one epoch = PPO._ppo_batch_train -------------------------------------------------------------------
     def run_epoch(self, ds):

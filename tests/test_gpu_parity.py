@@ -382,3 +382,20 @@ def test_update_vs_oracle_humanoid_shape():
         for k, v in obj.state_dict().items():
             np.testing.assert_allclose(v.cpu().numpy(), ref_state[f"{net}/param/{k}"], rtol=1e-4, atol=1e-6, err_msg=k)
     np.testing.assert_allclose(ds.values.cpu().numpy(), host["values"], rtol=1e-4, atol=1e-5)
+
+
+# ----------------------------------------------------------------------------------------- P5 / multi-GPU
+@pytest.mark.parametrize("discrete", [False, True])
+def test_two_rank_update_matches_multirank_oracle(discrete):
+    """DD-PPO step on 2 GPUs (NCCL all-reduce inside the captured graph) against the multi-rank oracle."""
+    import os, subprocess, sys
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    env = dict(os.environ, PPOAF_MG_DISCRETE="1" if discrete else "0")
+    port = 29500 + os.getpid() % 1000
+    res = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2",
+                          "--master-addr", "127.0.0.1", "--master-port", str(port),
+                          os.path.join(root, "tests", "multi_gpu_worker.py")], env=env, capture_output=True, text=True,
+                         timeout=600)
+    assert res.returncode == 0 and "MULTI_GPU_CHECK PASS" in res.stdout, res.stdout[-3000:] + res.stderr[-3000:]
