@@ -150,3 +150,9 @@ extern "C" int ppoaf_mlp_forward(const ppoaf_mlp_desc* net, const float* params,
     }
     return 0;
 }
+
+#ifdef PPOAF_GEMM_TIMING
+extern "C" int ppoaf_debug_gemm_stamps(long long* out_host) {
+    return cudaMemcpyFromSymbol(out_host, ppoaf::g_gemm_stamps, sizeof(long long) * 16) == cudaSuccess ? 0 : 1;
+}
+#endif

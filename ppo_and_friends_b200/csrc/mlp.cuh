@@ -152,9 +152,17 @@ __device__ __forceinline__ void load_frag(float (&f)[8][4], const float* tile, i
     }
 }
 
+#ifdef PPOAF_GEMM_TIMING
+__device__ long long g_gemm_stamps[16];
+#define PPOAF_STAMP(k) do { if (blockIdx.x == 0 && threadIdx.x == 0) g_gemm_stamps[k] = clock64(); } while (0)
+#else
+#define PPOAF_STAMP(k) do {} while (0)
+#endif
+
 template <bool A_RC, bool B_RC, int VA, int VB, int EPI>
 __device__ __forceinline__ void gemm_tile(const GemmProblem& g, int tile, int64_t idx_off, float* smem) {
     const int tid = threadIdx.x;
+    PPOAF_STAMP(1);
     const int grp = tid >> 5, lane = tid & 31;
     const int tx = lane & 7, ty = lane >> 3;                  // 8 column-lanes x 4 row-lanes per warp
     const int m0 = (tile / g.tiles_n) * kBM, n0 = (tile % g.tiles_n) * kBN;
@@ -172,6 +180,7 @@ __device__ __forceinline__ void gemm_tile(const GemmProblem& g, int tile, int64_
     };
 #pragma unroll 1
     for (int s = 0; s < kStages - 1; ++s) issue(s);
+    PPOAF_STAMP(2);
 
     float acc[8][8];
 #pragma unroll
@@ -185,6 +194,7 @@ __device__ __forceinline__ void gemm_tile(const GemmProblem& g, int tile, int64_
     for (int c = 0; c < n_chunks; ++c) {
         cp_async_wait<kStages - 2>();
         __syncthreads();                       // chunk c has landed for everyone; chunk c-1's stage is free
+        if (c == 0) PPOAF_STAMP(3);
         issue(c + kStages - 1);
         const float* a_tile = smem + (c % kStages) * kStageFloats;
         const float* b_tile = a_tile + kAFloats;
@@ -204,8 +214,10 @@ __device__ __forceinline__ void gemm_tile(const GemmProblem& g, int tile, int64_
                 }
         }
     }
+    PPOAF_STAMP(4);
     cp_async_wait<0>();
     __syncthreads();                           // pipeline memory is reused for the split-K reduction
+    PPOAF_STAMP(5);
 
     float* red = smem;                         // [8 groups][32][65]
 #pragma unroll
@@ -221,6 +233,7 @@ __device__ __forceinline__ void gemm_tile(const GemmProblem& g, int tile, int64_
         }
     }
     __syncthreads();
+    PPOAF_STAMP(6);
 
     // 2048 outputs / 512 threads: thread handles row r, columns c4 .. c4+3 (one LDS.128 per K-group)
     static_assert(kBM * kBN / kThreads == 4, "epilogue mapping assumes 4 outputs per thread");
@@ -255,6 +268,7 @@ __device__ __forceinline__ void gemm_tile(const GemmProblem& g, int tile, int64_
             }
         }
     }
+    PPOAF_STAMP(7);
     if constexpr (EPI == EPI_BWD_W) {
         if (g.sq_out) {                        // per-tile sum of squares -> gradient-norm clip without a norm pass
             __shared__ double s_sq[kThreads / 32];
@@ -273,6 +287,7 @@ __device__ __forceinline__ void gemm_tile(const GemmProblem& g, int tile, int64_
 
 __global__ void __launch_bounds__(kThreads) grouped_gemm_kernel(const GroupedGemmArgs args) {
     extern __shared__ __align__(16) float smem[];
+    PPOAF_STAMP(0);
     int p = 0;
 #pragma unroll
     for (int i = 1; i < kMaxGroup; ++i)
