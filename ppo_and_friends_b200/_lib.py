@@ -61,6 +61,8 @@ _SIGNATURES = {
     "ppoaf_device_info": (C.c_int, [C.POINTER(C.c_int)] * 3),
     "ppoaf_build_flat_map": (C.c_int, [_P, _P, _P, _P, _P, C.c_int32, C.c_int32, C.c_int64, _P, _P, _P]),
     "ppoaf_runtime_init": (C.c_int, []),
+    "ppoaf_set_gemm_backend": (C.c_int, [C.c_int]),
+    "ppoaf_get_gemm_backend": (C.c_int, []),
     "ppoaf_gather_rows": (C.c_int, [_P, C.c_int64, _P, C.c_int, _P, C.c_int64, C.c_int64, _P]),
     "ppoaf_segscan_workspace_bytes": (C.c_size_t, [C.c_int64]),
     "ppoaf_gae_rtg_segscan": (C.c_int, [_P, _P, _P, _P, _P, _P, C.c_int32, C.c_int64, C.c_double, C.c_double,

@@ -5,11 +5,14 @@
 namespace ppoaf {
 
 // mlp.cu — grouped GEMM launches (all GEMMs of one phase of the minibatch step in ONE launch)
+enum { GEMM_BACKEND_FFMA = 0, GEMM_BACKEND_TCGEN05 = 1 };
+int gemm_backend();             // PPOAF_GEMM=ffma|tcgen05 (default tcgen05: 3xTF32 tensor-core tiles)
 struct GroupedGemmArgs;
 struct GemmGroup {
     GroupedGemmArgs* args;      // owned
     int n_tiles;
-    GemmGroup();
+    int backend;
+    explicit GemmGroup(int backend);
     ~GemmGroup();
     GemmGroup(const GemmGroup&) = delete;
     GemmGroup& operator=(const GemmGroup&) = delete;
@@ -24,7 +27,7 @@ struct GemmGroup {
                        int in, int out, double* sq_out);
     int launch(const int32_t* cursor, int cursor_stride, cudaStream_t s);
 };
-int backward_w_tiles(int in, int out);
+int backward_w_tiles(int in, int out, int backend);
 void configure_gemm_kernels();
 int64_t param_layout(const ppoaf_mlp_desc* net, int32_t log_std_dim, int64_t* offsets);
 int check_mlp_desc(const ppoaf_mlp_desc* net, const char* who);

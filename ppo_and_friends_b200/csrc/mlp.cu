@@ -1,7 +1,8 @@
 // Host-side launchers for the MLP layer kernels (mlp.cuh), the flat parameter layout and the
 // forward-only entry point.
-#include "mlp.cuh"
+#include "umma.cuh"
 #include "internal.h"
+#include <stdlib.h>
 
 namespace ppoaf {
 
@@ -12,17 +13,22 @@ static inline bool vec4_ok(const float* p, int ld, int contig_extent) {
 // Called from ppoaf_runtime_init so that no attribute call happens inside a stream capture.
 void configure_gemm_kernels() {
     cudaFuncSetAttribute(grouped_gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, int(kGemmSmemBytes));
+    cudaFuncSetAttribute(umma::umma_grouped_gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                         int(umma::kUmmaSmemBytes));
 }
 
-GemmGroup::GemmGroup() : args(new GroupedGemmArgs()), n_tiles(0) { args->n_problems = 0; }
+static inline int tile_m(int backend) { return backend == GEMM_BACKEND_TCGEN05 ? umma::kUM : kBM; }
+static inline int tile_n(int backend) { return backend == GEMM_BACKEND_TCGEN05 ? umma::kUN : kBN; }
+
+GemmGroup::GemmGroup(int backend_) : args(new GroupedGemmArgs()), n_tiles(0), backend(backend_) { args->n_problems = 0; }
 GemmGroup::~GemmGroup() { delete args; }
 
 static GemmProblem* next_problem(GemmGroup* grp, int M, int N) {
     GemmProblem* g = &grp->args->p[grp->args->n_problems++];
     memset(g, 0, sizeof(*g));
-    g->tiles_n = (N + kBN - 1) / kBN;
+    g->tiles_n = (N + tile_n(grp->backend) - 1) / tile_n(grp->backend);
     g->tile_begin = grp->n_tiles;
-    grp->n_tiles += g->tiles_n * ((M + kBM - 1) / kBM);
+    grp->n_tiles += g->tiles_n * ((M + tile_m(grp->backend) - 1) / tile_m(grp->backend));
     return g;
 }
 
@@ -44,7 +50,9 @@ void GemmGroup::add_backward_x(const float* dZ, const float* W, const float* Xac
     g->flavour = EPI_BWD_X * 4 + (vec4_ok(dZ, out, out) ? 2 : 0) + (vec4_ok(W, in, in) ? 1 : 0);
 }
 
-int backward_w_tiles(int in, int out) { return ((in + kBN - 1) / kBN) * ((out + kBM - 1) / kBM); }
+int backward_w_tiles(int in, int out, int backend) {
+    return ((in + tile_n(backend) - 1) / tile_n(backend)) * ((out + tile_m(backend) - 1) / tile_m(backend));
+}
 
 int GemmGroup::add_backward_w(const float* dZ, const float* X, int ldx, const int64_t* idx, float* dW, float* db,
                               int rows, int in, int out, double* sq_out) {
@@ -53,15 +61,20 @@ int GemmGroup::add_backward_w(const float* dZ, const float* X, int ldx, const in
     g->M = out; g->N = in; g->K = rows;
     g->idxB = idx; g->dbias = db; g->sq_out = sq_out;
     g->flavour = EPI_BWD_W * 4 + (vec4_ok(dZ, out, out) ? 2 : 0) + (vec4_ok(X, ldx, in) ? 1 : 0);
-    return backward_w_tiles(in, out);
+    return backward_w_tiles(in, out, backend);
 }
 
 int GemmGroup::launch(const int32_t* cursor, int cursor_stride, cudaStream_t s) {
     if (n_tiles == 0) return 0;
     args->cursor = cursor;
     args->cursor_stride = cursor_stride;
-    grouped_gemm_kernel<<<n_tiles, kThreads, kGemmSmemBytes, s>>>(*args);
-    PPOAF_CHECK_LAUNCH("grouped_gemm_kernel");
+    if (backend == GEMM_BACKEND_TCGEN05) {
+        umma::umma_grouped_gemm_kernel<<<n_tiles, umma::kUThreads + 32, umma::kUmmaSmemBytes, s>>>(*args);
+        PPOAF_CHECK_LAUNCH("umma_grouped_gemm_kernel");
+    } else {
+        grouped_gemm_kernel<<<n_tiles, kThreads, kGemmSmemBytes, s>>>(*args);
+        PPOAF_CHECK_LAUNCH("grouped_gemm_kernel");
+    }
     return 0;
 }
 
@@ -74,6 +87,17 @@ __global__ void softmax_rows_kernel(float* __restrict__ y, int rows, int n) {
     float s = 0.f;
     for (int j = 0; j < n; ++j) { const float e = expf(p[j] - mx); p[j] = e; s += e; }
     for (int j = 0; j < n; ++j) p[j] = p[j] / s;
+}
+
+// Backend of the grouped GEMM launches: FFMA tiles (default: faster at B = 128..512) or the
+// tcgen05 3xTF32 tiles (PPOAF_GEMM=tcgen05 or ppoaf_set_gemm_backend(1)).
+static int g_backend = -1;
+int gemm_backend() {
+    if (g_backend < 0) {
+        const char* e = getenv("PPOAF_GEMM");
+        g_backend = (e && (strcmp(e, "tcgen05") == 0 || strcmp(e, "umma") == 0)) ? GEMM_BACKEND_TCGEN05 : GEMM_BACKEND_FFMA;
+    }
+    return g_backend;
 }
 
 int64_t param_layout(const ppoaf_mlp_desc* net, int32_t log_std_dim, int64_t* offsets) {
@@ -137,7 +161,7 @@ extern "C" int ppoaf_mlp_forward(const ppoaf_mlp_desc* net, const float* params,
     for (int l = 0; l < net->n_layers; ++l) {
         const bool last = l + 1 == net->n_layers;
         float* out = last ? y : buf[l & 1];
-        GemmGroup grp;
+        GemmGroup grp(gemm_backend());
         grp.add_forward(in, net->dims[l], in_idx, params + off[2 * l], params + off[2 * l + 1], out, n_rows,
                         net->dims[l], net->dims[l + 1], last ? PPOAF_ACT_IDENTITY : net->activation);
         if (grp.launch(nullptr, 0, s)) return 2;
@@ -156,3 +180,10 @@ extern "C" int ppoaf_debug_gemm_stamps(long long* out_host) {
     return cudaMemcpyFromSymbol(out_host, ppoaf::g_gemm_stamps, sizeof(long long) * 16) == cudaSuccess ? 0 : 1;
 }
 #endif
+
+extern "C" int ppoaf_set_gemm_backend(int backend) {
+    PPOAF_CHECK_ARG(backend == GEMM_BACKEND_FFMA || backend == GEMM_BACKEND_TCGEN05, "ppoaf_set_gemm_backend: 0 = ffma, 1 = tcgen05");
+    g_backend = backend;
+    return 0;
+}
+extern "C" int ppoaf_get_gemm_backend(void) { return gemm_backend(); }

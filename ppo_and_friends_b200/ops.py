@@ -30,6 +30,11 @@ def runtime_init():
     check(load().ppoaf_runtime_init(), "ppoaf_runtime_init")
 
 
+def set_gemm_backend(name):
+    """'ffma' (default) or 'tcgen05' (3xTF32 tensor-core tiles); applies to engines created afterwards."""
+    check(load().ppoaf_set_gemm_backend({'ffma': 0, 'tcgen05': 1}[name]), 'ppoaf_set_gemm_backend')
+
+
 def device_info():
     a, b, c = C.c_int(), C.c_int(), C.c_int()
     check(load().ppoaf_device_info(C.byref(a), C.byref(b), C.byref(c)), "ppoaf_device_info")

@@ -19,6 +19,15 @@ pytestmark = pytest.mark.gpu
 SEG_CASES = ["seg_single", "seg_multi", "seg_bsclip", "seg_nogae", "seg_dynclip", "seg_noclip", "seg_long"]
 
 
+@pytest.fixture(params=["ffma", "tcgen05"])
+def gemm_backend(request):
+    """Run a test on both engines of the MLP GEMM phases (FFMA tiles; tcgen05 3xTF32 tensor-core tiles)."""
+    from ppo_and_friends_b200 import ops
+    ops.set_gemm_backend(request.param)
+    yield request.param
+    ops.set_gemm_backend("ffma")
+
+
 def dev(x, dtype=None):
     t = torch.as_tensor(np.ascontiguousarray(x))
     if dtype is not None:
@@ -213,7 +222,7 @@ def test_normalize_clip_vs_oracle(n, dim):
 @pytest.mark.parametrize("dims,act,rows", [([8, 64, 64, 64, 2], "leaky_relu", 512), ([376, 256, 256, 256, 17], "tanh", 512),
                                            ([18, 128, 128, 128, 5], "leaky_relu", 128), ([54, 256, 256, 256, 1], "relu", 130),
                                            ([4, 128, 128, 128, 2], "leaky_relu", 3), ([5, 3], "tanh", 9)])
-def test_mlp_forward_vs_torch_fp32(dims, act, rows):
+def test_mlp_forward_vs_torch_fp32(dims, act, rows, gemm_backend):
     from oracle.update import ACTIVATIONS
     from ppo_and_friends_b200 import _lib, ops
     torch.manual_seed(sum(dims))
@@ -314,7 +323,7 @@ def policy_from_update_golden(g):
 
 @pytest.mark.parametrize("name", UPD_CASES)
 @pytest.mark.parametrize("use_graphs", [True, False])
-def test_update_matches_reference(name, use_graphs, monkeypatch):
+def test_update_matches_reference(name, use_graphs, monkeypatch, gemm_backend):
     from ppo_and_friends_b200.ppo import PPOUpdateState, _Loader, ppo_batch_train
     monkeypatch.setenv("PPOAF_NO_GRAPH", "0" if use_graphs else "1")
     g = load_golden(name)
@@ -344,7 +353,7 @@ def test_update_matches_reference(name, use_graphs, monkeypatch):
         np.testing.assert_allclose(ds.values.cpu().numpy(), g[f"ep{ep}/dataset_values"], rtol=1e-4, atol=1e-5)
 
 
-def test_update_vs_oracle_humanoid_shape():
+def test_update_vs_oracle_humanoid_shape(gemm_backend):
     """BASELINE config 4 network shapes (376-256^3-17 / 376-256^3-1, Tanh, B=512) against the torch-CPU oracle."""
     from oracle.update import OracleUpdater
     from ppo_and_friends_b200.ppo import PPOUpdateState, _Loader, ppo_batch_train
