@@ -456,8 +456,15 @@ def main():
         mb = microbench_c2(pk)
         line["microbench"] = mb
         dom = max(mb["pieces"].items(), key=lambda kv: kv[1]["ms"])
+        traffic = None
+        tpath = os.path.join(ROOT, "profiles", "r01_c2_traffic.json")      # dram bytes per launch from the ncu --set full capture
+        if os.path.exists(tpath):
+            k = json.load(open(tpath))["kernels"].get(dom[0])
+            if k:
+                traffic = k["dram_bytes_read"] + k["dram_bytes_write"]
         line["roofline"] = {"bound": "hbm", "achieved": dom[1]["gbs"], "peak": pk["hbm_gbs"], "unit": "GB/s",
-                            "frac": dom[1]["gbs"] / pk["hbm_gbs"], "traffic": None, "kernel": dom[0],
+                            "frac": dom[1]["gbs"] / pk["hbm_gbs"], "traffic": traffic, "algorithmic_bytes": dom[1]["bytes"],
+                            "kernel": dom[0],
                             "note": f"dominant HBM kernel of the GAE+normalisation microbench; peak = {pk['source']} copy bandwidth"}
     else:
         line["roofline"] = line["roofline_update"]

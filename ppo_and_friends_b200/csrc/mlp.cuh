@@ -93,32 +93,68 @@ __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commi
 template <int N>
 __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
 
-// Issue the cp.async's of one K chunk of one operand (OUT x 64 floats) into its shared tile.
+// Per-thread plan for the cp.async's of one operand (OUT x 64 floats per K chunk): everything that does not
+// depend on the chunk (shared-memory offsets, gathered row pointers, bounds) is computed once.
 //   RC (reduction-contiguous in global): tile[out][r], element P[row(out0+o)*ld + r0 + r]
 //   OC (output-contiguous in global):    tile[r][out], element P[row(r0+r)*ld + out0 + o]
 template <int OUT, bool RC, int V>
-__device__ __forceinline__ void load_chunk(float* tile, const float* __restrict__ P, int ld,
-                                           const int64_t* __restrict__ idx, int out0, int out_ext, int r0,
-                                           int red_ext, int tid) {
-    constexpr int LD_OC = OUT + 4;
-    constexpr int SLOTS = OUT * kBK / V / kThreads;
+struct ChunkLoader {
+    static constexpr int LD_OC = OUT + 4;
+    static constexpr int SLOTS = OUT * kBK / V / kThreads;
     static_assert(OUT * kBK / V % kThreads == 0, "slot count");
-#pragma unroll     // unrolled on purpose: the (gathered) row-index loads of all slots must be in flight together
-    for (int s = 0; s < SLOTS; ++s) {
-        const int slot = tid + s * kThreads;
-        int o, r;
-        if constexpr (RC) { o = slot / (kBK / V); r = (slot % (kBK / V)) * V; }
-        else              { r = slot / (OUT / V); o = (slot % (OUT / V)) * V; }
-        const int go = out0 + o, gr = r0 + r;
-        const bool ok = go < out_ext && gr < red_ext;
-        const float* src = P;
-        if (ok) {
-            const int row_sel = RC ? go : gr, col_sel = RC ? gr : go;
-            const int64_t row = idx ? idx[row_sel] : int64_t(row_sel);
-            src = P + row * ld + col_sel;
+    const float* src[SLOTS];     // RC: row base + r ; OC: P + o (row added per chunk)
+    int dst[SLOTS];              // float offset inside the tile
+    int rr[SLOTS];               // reduction index of the slot inside a chunk
+    bool ok[SLOTS];              // RC: row in range ; OC: output column in range
+    const float* P; const int64_t* idx; int ld;
+
+    __device__ __forceinline__ void plan(const float* __restrict__ P_, int ld_, const int64_t* __restrict__ idx_,
+                                         int out0, int out_ext, int tid) {
+        P = P_; idx = idx_; ld = ld_;
+#pragma unroll
+        for (int s = 0; s < SLOTS; ++s) {
+            const int slot = tid + s * kThreads;
+            int o, r;
+            if constexpr (RC) { o = slot / (kBK / V); r = (slot % (kBK / V)) * V; }
+            else              { r = slot / (OUT / V); o = (slot % (OUT / V)) * V; }
+            rr[s] = r;
+            dst[s] = RC ? o * kLdRC + r : r * LD_OC + o;
+            const int go = out0 + o;
+            ok[s] = go < out_ext;
+            if constexpr (RC) {
+                const int64_t row = ok[s] ? (idx ? idx[go] : int64_t(go)) : 0;
+                src[s] = P + row * ld + r;
+            } else {
+                src[s] = P + go;
+            }
         }
-        float* dst = RC ? tile + o * kLdRC + r : tile + r * LD_OC + o;
-        if constexpr (V == 4) cp_async_16(dst, src, ok); else cp_async_4(dst, src, ok);
+    }
+    __device__ __forceinline__ void issue(float* tile, int r0, int red_ext) const {
+#pragma unroll
+        for (int s = 0; s < SLOTS; ++s) {
+            const int gr = r0 + rr[s];
+            const bool valid = ok[s] && gr < red_ext;
+            const float* p = P;
+            if (valid) {
+                if constexpr (RC) p = src[s] + r0;
+                else p = src[s] + (idx ? idx[gr] : int64_t(gr)) * ld;
+            }
+            if constexpr (V == 4) cp_async_16(tile + dst[s], p, valid); else cp_async_4(tile + dst[s], p, valid);
+        }
+    }
+};
+
+__device__ __forceinline__ float fast_tanh(float x) {
+    // tanh(x) = 1 - 2 / (exp(2x) + 1); ex2/rcp based, absolute error ~2e-7 (the epilogues' hot math)
+    const float t = __expf(2.f * x);
+    return 1.f - __fdividef(2.f, t + 1.f);
+}
+__device__ __forceinline__ float act_fwd_fast(float x, int act) {
+    switch (act) {
+        case PPOAF_ACT_RELU: return x > 0.f ? x : 0.f;
+        case PPOAF_ACT_LEAKY_RELU: return x > 0.f ? x : 0.01f * x;
+        case PPOAF_ACT_TANH: return fast_tanh(x);
+        default: return x;
     }
 }
 
@@ -170,17 +206,31 @@ __device__ __forceinline__ void gemm_tile(const GemmProblem& g, int tile, int64_
     const int64_t* idxB = g.idxB ? g.idxB + idx_off : nullptr;
 
     const int n_chunks = (g.K + kBK - 1) / kBK;
+    ChunkLoader<kBM, A_RC, VA> la;
+    ChunkLoader<kBN, B_RC, VB> lb;
+    la.plan(g.A, g.lda, idxA, m0, g.M, tid);
+    lb.plan(g.B, g.ldb, idxB, n0, g.N, tid);
     auto issue = [&](int c) {
         if (c < n_chunks) {
             float* st = smem + (c % kStages) * kStageFloats;
-            load_chunk<kBM, A_RC, VA>(st, g.A, g.lda, idxA, m0, g.M, c * kBK, g.K, tid);
-            load_chunk<kBN, B_RC, VB>(st + kAFloats, g.B, g.ldb, idxB, n0, g.N, c * kBK, g.K, tid);
+            la.issue(st, c * kBK, g.K);
+            lb.issue(st + kAFloats, c * kBK, g.K);
         }
         cp_async_commit();
     };
 #pragma unroll 1
     for (int s = 0; s < kStages - 1; ++s) issue(s);
     PPOAF_STAMP(2);
+
+    // epilogue operands (bias / activation of the layer below) are fetched now: their latency hides behind the loop
+    const int er = tid / (kBN / 4), ec4 = (tid % (kBN / 4)) * 4;
+    float epi[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+        const int n = n0 + ec4 + j;
+        if constexpr (EPI == EPI_FWD) { if (n < g.N) epi[j] = g.bias[n]; }
+        if constexpr (EPI == EPI_BWD_X) { if (n < g.N && m0 + er < g.M) epi[j] = g.aux[int64_t(m0 + er) * g.ldaux + n]; }
+    }
 
     float acc[8][8];
 #pragma unroll
@@ -237,7 +287,7 @@ __device__ __forceinline__ void gemm_tile(const GemmProblem& g, int tile, int64_
 
     // 2048 outputs / 512 threads: thread handles row r, columns c4 .. c4+3 (one LDS.128 per K-group)
     static_assert(kBM * kBN / kThreads == 4, "epilogue mapping assumes 4 outputs per thread");
-    const int r = tid / (kBN / 4), c4 = (tid % (kBN / 4)) * 4;
+    const int r = er, c4 = ec4;
     const int m = m0 + r;
     float sq = 0.f;
     if (m < g.M) {
@@ -253,8 +303,8 @@ __device__ __forceinline__ void gemm_tile(const GemmProblem& g, int tile, int64_
             const int n = n0 + c4 + j;
             if (n >= g.N) continue;
             float o = o4[j];
-            if constexpr (EPI == EPI_FWD) o = act_fwd(o + g.bias[n], g.act);
-            if constexpr (EPI == EPI_BWD_X) o *= act_bwd_from_out(g.aux[int64_t(m) * g.ldaux + n], g.act);
+            if constexpr (EPI == EPI_FWD) o = act_fwd_fast(o + epi[j], g.act);
+            if constexpr (EPI == EPI_BWD_X) o *= act_bwd_from_out(epi[j], g.act);
             if constexpr (EPI == EPI_BWD_W) sq = fmaf(o, o, sq);
             g.C[int64_t(m) * g.ldc + n] = o;
         }

@@ -162,20 +162,6 @@ __device__ __forceinline__ uint64_t desc_base() {
 template <bool RC>
 __device__ __forceinline__ uint32_t kstep_units() { return RC ? 2u : 64u; }   // 16-byte units per k-step
 
-__device__ __forceinline__ float fast_tanh(float x) {
-    // tanh(x) = 1 - 2 / (exp(2x) + 1); ex2/rcp based, absolute error ~2e-7 (the epilogue's hot math)
-    const float t = __expf(2.f * x);
-    return 1.f - __fdividef(2.f, t + 1.f);
-}
-__device__ __forceinline__ float act_fwd_fast(float x, int act) {
-    switch (act) {
-        case PPOAF_ACT_RELU: return x > 0.f ? x : 0.f;
-        case PPOAF_ACT_LEAKY_RELU: return x > 0.f ? x : 0.01f * x;
-        case PPOAF_ACT_TANH: return fast_tanh(x);
-        default: return x;
-    }
-}
-
 // Warp roles: warps 0..7 stage operands and run the epilogue; warp 8 (one lane) issues the MMAs.
 //   full[s]  : 8 arrivals (one per staging warp, after its stores + proxy fence)  -> MMA warp may read stage s
 //   free[s]  : tcgen05.commit                                                     -> stage s may be overwritten

@@ -408,3 +408,63 @@ def test_two_rank_update_matches_multirank_oracle(discrete):
                           os.path.join(root, "tests", "multi_gpu_worker.py")], env=env, capture_output=True, text=True,
                          timeout=600)
     assert res.returncode == 0 and "MULTI_GPU_CHECK PASS" in res.stdout, res.stdout[-3000:] + res.stderr[-3000:]
+
+
+# ----------------------------------------------------------------------------------------- A7 / P6 / P8
+def test_dataset_getitem_and_len_match_reference_rows():
+    """PPODataset.__len__/__getitem__ (utils/episode_info.py:916-952): the 13-tuple of row idx."""
+    g = load_golden("seg_multi")
+    ro = rollout_from_golden(g)
+    pol = make_policy(ro, **policy_kwargs_from_golden(g))
+    ds = run_device_rollout(pol, ro)
+    assert len(ds) == len(g["advantages"])
+    for idx in (0, 7, len(ds) - 1):
+        item = ds[idx]
+        assert len(item) == 13 and item[12] == idx
+        assert np.array_equal(item[0].cpu().numpy(), g["critic_observations"][idx])
+        assert np.array_equal(item[1].cpu().numpy(), g["observations"][idx])
+        assert np.array_equal(item[2].cpu().numpy(), g["next_observations"][idx])
+        assert np.array_equal(item[3].cpu().numpy(), g["raw_actions"][idx])
+        assert np.array_equal(item[4].cpu().numpy(), g["actions"][idx])
+        assert float(item[6]) == float(g["log_probs"][idx])
+
+
+def test_epoch_loop_kl_early_stop_and_lr_schedule():
+    """train_policies = the epoch loop of PPO.learn (ppo.py:2201-2232): KL early stop after an epoch whose
+    `kl avg` exceeds target_kl, and hyper-parameters re-read every epoch (row P8) without re-capturing graphs."""
+    from oracle.update import OracleUpdater
+    from ppo_and_friends_b200.ppo import PPOUpdateState, train_policies
+    from ppo_and_friends_b200.synthetic import make_rollout
+    ro = make_rollout(seed=91, T=32, E=8, obs_dim=6, act_dim=2, max_ts_per_ep=8, obs_scale=False)
+    torch.manual_seed(2)
+
+    class Sched:                      # a scheduler-like callable (utils/schedulers.py): the lr changes between epochs
+        def __init__(self): self.v = 1e-3
+        def finalize(self, status_dict): pass
+        def __call__(self): return self.v
+
+    lr = Sched()
+    pol = make_policy(ro, act="tanh", actor_hidden=16, critic_hidden=16, lr=lr, target_kl=1e9)
+    ds = run_device_rollout(pol, ro)
+    host = {k: getattr(ds, k).cpu().numpy().copy() for k in ("critic_observations", "observations", "raw_actions",
+                                                               "advantages", "log_probs", "rewards_to_go", "values")}
+    oracle = OracleUpdater({k: v.cpu().numpy() for k, v in pol.actor.state_dict().items()},
+                           {k: v.cpu().numpy() for k, v in pol.critic.state_dict().items()}, "tanh", False, lr=1e-3)
+    state = PPOUpdateState({"pol": pol}, batch_size=64, epochs_per_iter=1)
+    torch.manual_seed(3)
+    assert train_policies(state) == {"pol": 1}
+    oracle.batch_train([host], [pol._engine._perm_dev.cpu().numpy()], 64)
+    lr.v = 2.5e-4                                                        # schedule step between iterations
+    oracle.lr = 2.5e-4
+    train_policies(state)
+    oracle.batch_train([host], [pol._engine._perm_dev.cpu().numpy()], 64)
+    ref = oracle.state()
+    for net, obj in (("actor", pol.actor), ("critic", pol.critic)):
+        for k, v in obj.state_dict().items():
+            np.testing.assert_allclose(v.cpu().numpy(), ref[f"{net}/param/{k}"], rtol=1e-4, atol=1e-6, err_msg=k)
+    # KL early stop: random old log-probs give a large positive KL, so a low target stops after the first epoch
+    state.epochs_per_iter = 5
+    pol.target_kl = -1e9
+    assert train_policies(state) == {"pol": 1}
+    pol.target_kl = 1e9
+    assert train_policies(state) == {"pol": 5}
