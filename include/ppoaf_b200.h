@@ -217,6 +217,26 @@ int ppoaf_head_evaluate(int32_t head, const float* actor_out, int32_t pred_dim, 
                         float min_std, const void* actions, int32_t act_dim, int32_t n_rows,
                         float* log_prob_out, float* entropy_out, void* stream);
 
+/* ------------------------------------------------------------------------------------------
+ * P5  Gradient all-reduce over NVLink peer memory FUSED with clip + Adam (R > 1 on one node).
+ * Replaces mpi_avg_gradients (utils/mpi_utils.py:89-111) + clip_grad_norm_ + Adam.step
+ * (policies/ppo_policy.py:1032-1055) with ONE kernel per rank: cross-GPU flag barrier, one-shot
+ * reduce of the R peer gradient buffers in rank order (bit-identical on every rank), gradient norm,
+ * clip, Adam.  Buffers come from ppoaf_peer_alloc (cudaMalloc) and are shared with CUDA IPC
+ * handles that the host exchanges through torch.distributed; gradients are double-buffered by step
+ * parity so one barrier per step suffices.  `ctrl`: local zeroed scratch of ppoaf_peer_ctrl_bytes().
+ * ---------------------------------------------------------------------------------------- */
+int    ppoaf_peer_alloc(size_t bytes, void** out);
+int    ppoaf_peer_free(void* p);
+int    ppoaf_peer_export(void* p, uint8_t* handle64);
+int    ppoaf_peer_import(const uint8_t* handle64, void** out);
+int    ppoaf_peer_close(void* p);
+size_t ppoaf_peer_ctrl_bytes(void);
+int    ppoaf_peer_allreduce_adam(const void* const* peer_grads, void* const* peer_flags, int32_t n_ranks,
+                                 int32_t my_rank, float* params, float* adam_m, float* adam_v,
+                                 int64_t* adam_step, int32_t* mb_cursor, const double* hparams,
+                                 int64_t n_actor, int64_t n_critic, void* ctrl, void* stream);
+
 /* Stand-alone pieces (unit-parity entry points; the composite calls the same kernels). */
 int ppoaf_clip_adam_step(float* params, const float* grads, float* adam_m, float* adam_v,
                          int64_t* adam_step, const double* hparams, int64_t n_actor, int64_t n_critic,

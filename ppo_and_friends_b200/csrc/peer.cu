@@ -1,0 +1,259 @@
+// Gradient all-reduce over NVLink peer memory FUSED with the gradient-norm clip and Adam
+// (replaces: mpi_avg_gradients utils/mpi_utils.py:89-111 + clip_grad_norm_ + Adam.step,
+// policies/ppo_policy.py:1032-1055; on the NCCL path that is all-reduce + norm pass + Adam = 3 launches).
+//
+// Every rank runs this kernel on its own GPU at the same point of the step.  Gradients live in buffers that
+// are mapped into every peer (CUDA IPC over NVSwitch), double-buffered by step parity:
+//   1. cross-GPU barrier: each rank publishes "my gradient buffer for step t is complete" by writing t into
+//      flag[my_rank] of EVERY peer (st.release.sys over NVLink) and spins on its LOCAL flags until all R
+//      ranks have published t;
+//   2. one-shot reduce: every thread sums its float4 slots over the R peer buffers in rank order (so every rank
+//      gets bit-identical sums), keeps them in registers, and accumulates per-network sums of squares;
+//   3. local grid barrier (all CTAs are co-resident: grid <= #SMs), fixed-order fold of the CTA partials;
+//   4. clip coefficient, bias corrections, Adam on the register-held gradient -> params, m, v (local).
+// Because the buffers alternate with step parity, a buffer is rewritten only two steps later, after every
+// peer has passed barrier 1 of the step in between — no second cross-GPU barrier is needed.
+// A spin that exceeds ~2 s sets an error flag and returns instead of hanging the GPU.
+#include "internal.h"
+
+namespace ppoaf {
+
+constexpr int kPeerThreads = 256;
+constexpr int kPeerMaxRanks = 8;
+constexpr int kPeerMaxVec = 8;            // float4 slots per thread held in registers
+constexpr long long kSpinLimit = 4000000000LL;   // ~2 s of SM clock
+
+struct PeerArgs {
+    const float* peer_grads[kPeerMaxRanks];   // gradient buffer of every rank for THIS parity (index = rank)
+    uint32_t* peer_flags[kPeerMaxRanks];      // flag array of every rank; element [src_rank] is written by src_rank
+    uint32_t* local_flags;                    // == peer_flags[my_rank]
+    int n_ranks, my_rank;
+};
+
+__device__ __forceinline__ void st_release_sys(uint32_t* p, uint32_t v) {
+    asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+__device__ __forceinline__ uint32_t ld_acquire_sys(const uint32_t* p) {
+    uint32_t v;
+    asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ uint32_t ld_acquire_gpu(const uint32_t* p) {
+    uint32_t v;
+    asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+
+// ctrl (local, zero-initialised): [0] epoch (cross-GPU barrier value of the last call), [1] local arrive counter,
+// [2] local generation, [3] ticket, [4] error flag
+__global__ void __launch_bounds__(kPeerThreads)
+peer_allreduce_adam_kernel(const PeerArgs pa, float* __restrict__ params, float* __restrict__ m, float* __restrict__ v,
+                           int64_t n_actor, int64_t n_total, const double* __restrict__ hp,
+                           int64_t* __restrict__ adam_step, int32_t* __restrict__ mb_cursor,
+                           double* __restrict__ partials, uint32_t* __restrict__ ctrl) {
+    __shared__ double s_scr[32];
+    __shared__ float s_f[8];
+    __shared__ int s_err;
+    const int tid = threadIdx.x;
+    const int R = pa.n_ranks;
+    const uint32_t epoch = ctrl[0] + 1;        // every CTA reads the value of the previous call (updated at the very end)
+    if (tid == 0) s_err = 0;
+
+    // ---- 1. cross-GPU barrier: publish, then wait for every rank's flag to reach `epoch` ----
+    if (blockIdx.x == 0 && tid < R) {
+        __threadfence_system();                // this rank's gradient writes (previous kernels) are visible system-wide
+        st_release_sys(pa.peer_flags[tid] + pa.my_rank, epoch);
+    }
+    if (tid < R) {
+        const long long t0 = clock64();
+        while (int32_t(ld_acquire_sys(pa.local_flags + tid) - epoch) < 0) {
+            if (clock64() - t0 > kSpinLimit) { s_err = 1; break; }
+        }
+    }
+    __syncthreads();
+    if (s_err) {                               // a peer never arrived: report instead of hanging
+        if (tid == 0) atomicExch(ctrl + 4, 1u);
+        return;
+    }
+
+    // ---- 2. one-shot reduce in rank order, gradient kept in registers ----
+    const int64_t nv = n_total / 4, na = n_actor / 4;
+    const int64_t stride = int64_t(gridDim.x) * blockDim.x;
+    float4 g[kPeerMaxVec];
+    double sa = 0.0, sc = 0.0;
+#pragma unroll
+    for (int k = 0; k < kPeerMaxVec; ++k) {
+        const int64_t i = int64_t(blockIdx.x) * blockDim.x + tid + k * stride;
+        g[k] = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (i < nv) {
+            float4 acc = reinterpret_cast<const float4*>(pa.peer_grads[0])[i];
+            for (int r = 1; r < R; ++r) {
+                const float4 x = reinterpret_cast<const float4*>(pa.peer_grads[r])[i];
+                acc.x += x.x; acc.y += x.y; acc.z += x.z; acc.w += x.w;
+            }
+            g[k] = acc;
+            const float q = fmaf(acc.x, acc.x, fmaf(acc.y, acc.y, fmaf(acc.z, acc.z, acc.w * acc.w)));
+            if (i < na) sa += double(q); else sc += double(q);
+        }
+    }
+    sa = block_sum(sa, s_scr);
+    sc = block_sum(sc, s_scr);
+
+    // ---- 3. local grid barrier + fixed-order fold of the CTA partials ----
+    if (tid == 0) {
+        partials[2 * blockIdx.x] = sa;
+        partials[2 * blockIdx.x + 1] = sc;
+        __threadfence();
+        const uint32_t gen = ld_acquire_gpu(ctrl + 2);
+        if (atomicAdd(ctrl + 1, 1u) == gridDim.x - 1) {
+            ctrl[1] = 0u;
+            __threadfence();
+            atomicAdd(ctrl + 2, 1u);           // release the generation
+        } else {
+            const long long t0 = clock64();
+            while (ld_acquire_gpu(ctrl + 2) == gen) {
+                if (clock64() - t0 > kSpinLimit) { s_err = 1; break; }
+            }
+        }
+    }
+    __syncthreads();
+    if (s_err) {
+        if (tid == 0) atomicExch(ctrl + 4, 2u);
+        return;
+    }
+    double ta = 0.0, tc = 0.0;
+    for (int b = tid; b < int(gridDim.x); b += blockDim.x) { ta += __ldcg(&partials[2 * b]); tc += __ldcg(&partials[2 * b + 1]); }
+    ta = block_sum(ta, s_scr);
+    tc = block_sum(tc, s_scr);
+
+    // ---- 4. scalars, then Adam on the register-held gradient ----
+    const int64_t t = *adam_step + 1;
+    if (tid == 0) {
+        const float inv_world = float(hp[PPOAF_HP_INV_WORLD]);
+        const float max_norm = float(hp[PPOAF_HP_GRAD_CLIP]);
+        float ca = 1.f, cc = 1.f;
+        if (max_norm >= 0.f) {                 // clip_grad_norm_ on the AVERAGED gradient
+            ca = fminf(max_norm / (float(sqrt(ta) * double(inv_world)) + 1e-6f), 1.f);
+            cc = fminf(max_norm / (float(sqrt(tc) * double(inv_world)) + 1e-6f), 1.f);
+        }
+        const double b1d = hp[PPOAF_HP_BETA1], b2d = hp[PPOAF_HP_BETA2];
+        s_f[0] = float(-(hp[PPOAF_HP_LR] / (1.0 - pow(b1d, double(t)))));
+        s_f[1] = float(sqrt(1.0 - pow(b2d, double(t))));
+        s_f[2] = float(1.0 - b1d);
+        s_f[3] = float(b2d);
+        s_f[4] = float(1.0 - b2d);
+        s_f[5] = float(hp[PPOAF_HP_ADAM_EPS]);
+        s_f[6] = ca;
+        s_f[7] = cc;
+    }
+    __syncthreads();
+    const float neg_step_size = s_f[0], bc2_sqrt = s_f[1], w1 = s_f[2], beta2 = s_f[3], w2 = s_f[4], eps = s_f[5];
+    const float inv_world = float(hp[PPOAF_HP_INV_WORLD]);
+    float4* p4 = reinterpret_cast<float4*>(params);
+    float4* m4 = reinterpret_cast<float4*>(m);
+    float4* v4 = reinterpret_cast<float4*>(v);
+#pragma unroll
+    for (int k = 0; k < kPeerMaxVec; ++k) {
+        const int64_t i = int64_t(blockIdx.x) * blockDim.x + tid + k * stride;
+        if (i >= nv) continue;
+        const float coef = i < na ? s_f[6] : s_f[7];
+        float4 pq = p4[i], mq = m4[i], vq = v4[i];
+        float gg[4] = {g[k].x, g[k].y, g[k].z, g[k].w}, p[4] = {pq.x, pq.y, pq.z, pq.w};
+        float mm[4] = {mq.x, mq.y, mq.z, mq.w}, vv[4] = {vq.x, vq.y, vq.z, vq.w};
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {          // same operation order as adam_update_kernel / torch's CPU kernels
+            const float gk = __fmul_rn(__fmul_rn(gg[j], inv_world), coef);
+            mm[j] = __fadd_rn(mm[j], __fmul_rn(w1, __fsub_rn(gk, mm[j])));
+            vv[j] = __fadd_rn(__fmul_rn(vv[j], beta2), __fmul_rn(__fmul_rn(w2, gk), gk));
+            const float denom = __fadd_rn(__fdiv_rn(__fsqrt_rn(vv[j]), bc2_sqrt), eps);
+            p[j] = __fadd_rn(p[j], __fdiv_rn(__fmul_rn(neg_step_size, mm[j]), denom));
+        }
+        p4[i] = make_float4(p[0], p[1], p[2], p[3]);
+        m4[i] = make_float4(mm[0], mm[1], mm[2], mm[3]);
+        v4[i] = make_float4(vv[0], vv[1], vv[2], vv[3]);
+    }
+    // ---- the last CTA to finish advances the counters (everyone has read adam_step / ctrl[0] by then) ----
+    __syncthreads();
+    if (tid == 0) {
+        __threadfence();
+        if (atomicAdd(ctrl + 3, 1u) == gridDim.x - 1) {
+            *adam_step = t;
+            if (mb_cursor) *mb_cursor += 1;
+            ctrl[0] = epoch;
+            ctrl[3] = 0u;
+        }
+    }
+}
+
+}  // namespace ppoaf
+
+using namespace ppoaf;
+
+// ---- peer-memory plumbing (cudaMalloc + CUDA IPC; the handles travel through torch.distributed) ----------
+extern "C" int ppoaf_peer_alloc(size_t bytes, void** out) {
+    PPOAF_CHECK_ARG(out != nullptr && bytes > 0, "ppoaf_peer_alloc: bad arguments");
+    cudaError_t e = cudaMalloc(out, bytes);
+    PPOAF_CHECK_ARG(e == cudaSuccess, "ppoaf_peer_alloc: cudaMalloc failed: %s", cudaGetErrorString(e));
+    e = cudaMemset(*out, 0, bytes);
+    PPOAF_CHECK_ARG(e == cudaSuccess, "ppoaf_peer_alloc: cudaMemset failed: %s", cudaGetErrorString(e));
+    return 0;
+}
+extern "C" int ppoaf_peer_free(void* p) {
+    cudaError_t e = cudaFree(p);
+    PPOAF_CHECK_ARG(e == cudaSuccess, "ppoaf_peer_free: %s", cudaGetErrorString(e));
+    return 0;
+}
+extern "C" int ppoaf_peer_export(void* p, uint8_t* handle64) {
+    static_assert(sizeof(cudaIpcMemHandle_t) == 64, "IPC handle size");
+    cudaIpcMemHandle_t h;
+    cudaError_t e = cudaIpcGetMemHandle(&h, p);
+    PPOAF_CHECK_ARG(e == cudaSuccess, "ppoaf_peer_export: cudaIpcGetMemHandle failed: %s", cudaGetErrorString(e));
+    memcpy(handle64, &h, 64);
+    return 0;
+}
+extern "C" int ppoaf_peer_import(const uint8_t* handle64, void** out) {
+    cudaIpcMemHandle_t h;
+    memcpy(&h, handle64, 64);
+    cudaError_t e = cudaIpcOpenMemHandle(out, h, cudaIpcMemLazyEnablePeerAccess);
+    PPOAF_CHECK_ARG(e == cudaSuccess, "ppoaf_peer_import: cudaIpcOpenMemHandle failed: %s", cudaGetErrorString(e));
+    return 0;
+}
+extern "C" int ppoaf_peer_close(void* p) {
+    cudaError_t e = cudaIpcCloseMemHandle(p);
+    PPOAF_CHECK_ARG(e == cudaSuccess, "ppoaf_peer_close: %s", cudaGetErrorString(e));
+    return 0;
+}
+
+extern "C" size_t ppoaf_peer_ctrl_bytes(void) { return size_t(sm_count()) * 2 * sizeof(double) + 256; }
+
+// peer_grads[r] / peer_flags[r]: pointers valid on THIS device for rank r's buffers (own rank: the local pointers).
+// ctrl: local zero-initialised scratch of ppoaf_peer_ctrl_bytes() bytes (CTA partials, then the barrier words).
+extern "C" int ppoaf_peer_allreduce_adam(const void* const* peer_grads, void* const* peer_flags, int32_t n_ranks,
+                                         int32_t my_rank, float* params, float* adam_m, float* adam_v,
+                                         int64_t* adam_step, int32_t* mb_cursor, const double* hparams,
+                                         int64_t n_actor, int64_t n_critic, void* ctrl, void* stream) {
+    PPOAF_CHECK_ARG(n_ranks >= 1 && n_ranks <= kPeerMaxRanks && my_rank >= 0 && my_rank < n_ranks,
+                    "ppoaf_peer_allreduce_adam: up to %d ranks", kPeerMaxRanks);
+    PPOAF_CHECK_ARG(n_actor % 4 == 0 && n_critic % 4 == 0, "ppoaf_peer_allreduce_adam: segments must be multiples of 4 floats");
+    const int64_t n_total = n_actor + n_critic;
+    int grid = sm_count();
+    const int64_t need = ceil_div64(n_total / 4, kPeerThreads);
+    if (need < grid) grid = int(need < 1 ? 1 : need);
+    PPOAF_CHECK_ARG(n_total / 4 <= int64_t(grid) * kPeerThreads * kPeerMaxVec,
+                    "ppoaf_peer_allreduce_adam: %lld parameters exceed the register-resident limit; use the NCCL path",
+                    (long long)n_total);
+    PeerArgs pa{};
+    for (int r = 0; r < n_ranks; ++r) {
+        pa.peer_grads[r] = static_cast<const float*>(peer_grads[r]);
+        pa.peer_flags[r] = static_cast<uint32_t*>(peer_flags[r]);
+    }
+    pa.local_flags = static_cast<uint32_t*>(peer_flags[my_rank]);
+    pa.n_ranks = n_ranks;
+    pa.my_rank = my_rank;
+    double* partials = static_cast<double*>(ctrl);
+    uint32_t* words = reinterpret_cast<uint32_t*>(static_cast<char*>(ctrl) + size_t(sm_count()) * 2 * sizeof(double));
+    peer_allreduce_adam_kernel<<<grid, kPeerThreads, 0, (cudaStream_t)stream>>>(pa, params, adam_m, adam_v, n_actor, n_total,
+                                                                               hparams, adam_step, mb_cursor, partials, words);
+    PPOAF_CHECK_LAUNCH("peer_allreduce_adam_kernel");
+    return 0;
+}

@@ -54,6 +54,13 @@ class UpdateEngine:
         self.use_graphs = (os.environ.get("PPOAF_NO_GRAPH", "0") != "1") if use_graphs is None else use_graphs
         # capturing the NCCL all-reduce inside the step graph is opt-in (PPOAF_GRAPH_COLLECTIVE=1)
         self.capture_collective = os.environ.get("PPOAF_GRAPH_COLLECTIVE", "0") == "1"
+        # R > 1: gradients are reduced over NVLink peer memory by the fused all-reduce + clip + Adam kernel
+        # (PPOAF_PEER=0 falls back to NCCL all-reduce + norm pass + Adam)
+        self.peer = None
+        self.step_parity = 0
+        if mpi_utils.get_num_procs() > 1 and os.environ.get("PPOAF_PEER", "1") != "0" and self.device.type == "cuda":
+            from .utils.peer import PeerGroup
+            self.peer = PeerGroup(policy.nets.n_actor + policy.nets.n_critic, self.device)
         nets = policy.nets
         cfg = _lib.UpdateCfg()
         cfg.actor, cfg.critic = nets.actor.desc, nets.critic.desc
@@ -94,7 +101,7 @@ class UpdateEngine:
         self.hparams.copy_(h, non_blocking=True)
 
     # -- buffers struct for a given dataset / minibatch size ---------------------------------------------
-    def _bufs(self, ds, rows):
+    def _bufs(self, ds, rows, parity=0):
         nets = self.policy.nets
         b = _lib.UpdateBufs()
         b.critic_obs, b.obs = ds.critic_observations.data_ptr(), ds.observations.data_ptr()
@@ -103,7 +110,8 @@ class UpdateEngine:
         b.rewards_to_go, b.values = ds.rewards_to_go.data_ptr(), ds.values.data_ptr()
         b.perm = self._perm_dev.data_ptr()
         b.mb_adv_stats, b.mb_val_stats = self._mb_adv_stats.data_ptr(), self._mb_val_stats.data_ptr()
-        b.params, b.grads = nets.flat_params.data_ptr(), nets.flat_grads.data_ptr()
+        grads = self.peer.grads[parity] if self.peer is not None else nets.flat_grads
+        b.params, b.grads = nets.flat_params.data_ptr(), grads.data_ptr()
         b.adam_m, b.adam_v, b.adam_step = nets.adam_m.data_ptr(), nets.adam_v.data_ptr(), nets.adam_step.data_ptr()
         b.hparams, b.epoch_stats = self.hparams.data_ptr(), self.epoch_stats.data_ptr()
         b.mb_cursor = self.mb_cursor.data_ptr()
@@ -122,8 +130,14 @@ class UpdateEngine:
         check(load().ppoaf_ppo_minibatch_apply(C.byref(self.cfg), C.byref(bufs), stream_ptr()),
               "ppoaf_ppo_minibatch_apply")
 
-    def _step_eager(self, bufs):
+    def _step_eager(self, bufs, parity=0):
         self._grads(bufs)
+        if self.peer is not None:
+            if bufs.batch > 1:
+                self.peer.allreduce_adam(parity, self.policy.nets, self.mb_cursor, self.hparams, stream_ptr())
+            else:
+                self._apply(bufs)                    # one-row minibatch: only the cursor advances
+            return
         if bufs.batch > 1:
             mpi_utils.mpi_avg_gradients(self.policy.nets.flat_grads)
         self._apply(bufs)
@@ -148,20 +162,24 @@ class UpdateEngine:
         return graph
 
     def _launch_step(self, ds, rows):
-        key = (rows, ds.observations.data_ptr(), ds.critic_observations.data_ptr(), ds.values.data_ptr(),
+        parity = self.step_parity if self.peer is not None else 0
+        if self.peer is not None and rows > 1:
+            self.step_parity ^= 1                      # the peer gradient buffers alternate every real step
+            self.policy.nets.flat_grads = self.peer.grads[parity]
+        key = (rows, parity, ds.observations.data_ptr(), ds.critic_observations.data_ptr(), ds.values.data_ptr(),
                ds.advantages.data_ptr())
         if not self.use_graphs or rows < 2:
-            self._step_eager(self._bufs(ds, rows))
+            self._step_eager(self._bufs(ds, rows, parity), parity)
             return
         g = self._graphs.get(key)
         if g is None:
-            if len(self._graphs) > 8:
+            if len(self._graphs) > 16:
                 self._graphs.clear()
-            bufs = self._bufs(ds, rows)
-            if mpi_utils.get_num_procs() == 1 or self.capture_collective:
-                g = (self._capture(lambda: self._step_eager(bufs)), None, bufs)
+            bufs = self._bufs(ds, rows, parity)
+            if mpi_utils.get_num_procs() == 1 or self.capture_collective or self.peer is not None:
+                g = (self._capture(lambda: self._step_eager(bufs, parity)), None, bufs)
             else:
-                # R > 1: two graphs with the NCCL all-reduce of the flat gradient enqueued between them
+                # NCCL path: two graphs with the all-reduce of the flat gradient enqueued between them
                 g = (self._capture(lambda: self._grads(bufs)), self._capture(lambda: self._apply(bufs)), bufs)
             self._graphs[key] = g
         g[0].replay()
@@ -222,6 +240,8 @@ def ppo_batch_train(ppo, data_loader, policy_id):
         mpi_utils.abort("ERROR: evaluate value or action prediction contains nan values!")
     if st[ST["BAD_RATIO"]] > 0:
         mpi_utils.abort("ERROR: ratios are nan or inf!")
+    if eng.peer is not None and eng.peer.error_flag() != 0:
+        mpi_utils.abort("ERROR: a rank did not reach the gradient exchange (peer barrier timed out)")
     sums = np.array([st[ST["COUNTER"]], st[ST["ENTROPY"]], st[ST["ACTOR_LOSS"]], st[ST["CRITIC_LOSS"]], st[ST["KL"]]])
     if mpi_utils.get_num_procs() > 1:                                   # ppo.py:2471-2475, one packed all-reduce
         t = torch.as_tensor(sums).to(policy.device)

@@ -1,0 +1,87 @@
+"""
+NVLink peer-memory group for the fused gradient all-reduce + clip + Adam (csrc/peer.cu).
+
+Each rank allocates two gradient buffers (step parity 0 / 1) and one flag array with cudaMalloc through the
+C ABI, exports CUDA IPC handles, and the handles are exchanged with `torch.distributed.all_gather_object`
+(any backend).  After `PeerGroup(...)` every rank holds device pointers to every peer's buffers.
+"""
+import ctypes as C
+
+import torch
+import torch.distributed as dist
+
+from .. import _lib
+from .._lib import check, load
+
+
+class _RawCudaBuffer:
+    """Exposes a raw device allocation to torch through __cuda_array_interface__ (no copy, no ownership)."""
+
+    def __init__(self, ptr, n_floats):
+        self.__cuda_array_interface__ = {"shape": (n_floats,), "typestr": "<f4", "data": (int(ptr), False), "version": 2}
+
+
+class PeerGroup:
+    def __init__(self, n_floats, device):
+        assert dist.is_initialized() and dist.get_world_size() > 1
+        lib = load()
+        self.rank, self.world = dist.get_rank(), dist.get_world_size()
+        self.n_floats = int(n_floats)
+        self.device = torch.device(device)
+        nbytes = (self.n_floats * 4 + 255) // 256 * 256
+        self._local = []
+        for _ in range(3):                                     # grads[0], grads[1], flags
+            p = C.c_void_p()
+            check(lib.ppoaf_peer_alloc(nbytes if len(self._local) < 2 else 256, C.byref(p)), "ppoaf_peer_alloc")
+            self._local.append(p.value)
+        handles = []
+        for p in self._local:
+            buf = C.create_string_buffer(64)
+            check(lib.ppoaf_peer_export(C.c_void_p(p), buf), "ppoaf_peer_export")
+            handles.append(buf.raw)
+        torch.cuda.synchronize(self.device)
+        gathered = [None] * self.world
+        dist.all_gather_object(gathered, handles)
+        self._opened = []
+        self.ptrs = []                                         # ptrs[r] = [grads0, grads1, flags] valid on this device
+        for r in range(self.world):
+            if r == self.rank:
+                self.ptrs.append(list(self._local))
+                continue
+            mine = []
+            for h in gathered[r]:
+                p = C.c_void_p()
+                check(lib.ppoaf_peer_import(h, C.byref(p)), "ppoaf_peer_import")
+                mine.append(p.value)
+                self._opened.append(p.value)
+            self.ptrs.append(mine)
+        self.grads = [torch.as_tensor(_RawCudaBuffer(self._local[k], self.n_floats), device=self.device) for k in range(2)]
+        self.ctrl = torch.zeros(lib.ppoaf_peer_ctrl_bytes(), dtype=torch.uint8, device=self.device)
+        self._grad_arrays = []
+        for k in range(2):
+            arr = (C.c_void_p * self.world)(*[self.ptrs[r][k] for r in range(self.world)])
+            self._grad_arrays.append(arr)
+        self._flag_array = (C.c_void_p * self.world)(*[self.ptrs[r][2] for r in range(self.world)])
+        dist.barrier()                                         # everyone has mapped everyone before first use
+
+    def allreduce_adam(self, parity, nets, mb_cursor, hparams, stream_ptr):
+        check(load().ppoaf_peer_allreduce_adam(
+            self._grad_arrays[parity], self._flag_array, self.world, self.rank, C.c_void_p(nets.flat_params.data_ptr()),
+            C.c_void_p(nets.adam_m.data_ptr()), C.c_void_p(nets.adam_v.data_ptr()), C.c_void_p(nets.adam_step.data_ptr()),
+            C.c_void_p(mb_cursor.data_ptr()), C.c_void_p(hparams.data_ptr()), nets.n_actor, nets.n_critic,
+            C.c_void_p(self.ctrl.data_ptr()), stream_ptr), "ppoaf_peer_allreduce_adam")
+
+    def error_flag(self):
+        off = load().ppoaf_peer_ctrl_bytes() - 256 + 16
+        return int(self.ctrl[off:off + 4].view(torch.int32).item())
+
+    def close(self):
+        lib = load()
+        torch.cuda.synchronize(self.device)
+        if dist.is_initialized():
+            dist.barrier()
+        for p in self._opened:
+            lib.ppoaf_peer_close(C.c_void_p(p))
+        for p in self._local:
+            lib.ppoaf_peer_free(C.c_void_p(p))
+        self._opened, self._local = [], []
