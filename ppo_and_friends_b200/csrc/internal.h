@@ -64,6 +64,12 @@ size_t loss_workspace_bytes(int max_batch, int act_dim);
 int launch_ppo_loss(const LossArgs& a, cudaStream_t s);
 
 // optim.cu
+// beta^t for the Adam bias corrections without a double pow() on the critical path: cache = (t, b1^t, b2^t) of the
+// previous step; one multiply when t advanced by one, pow() otherwise (first step, restored checkpoints).
+__device__ __forceinline__ void beta_powers(const double* cache, int64_t t, double b1, double b2, double& p1, double& p2) {
+    if (cache[0] == double(t - 1) && t > 1) { p1 = cache[1] * b1; p2 = cache[2] * b2; }
+    else { p1 = pow(b1, double(t)); p2 = pow(b2, double(t)); }
+}
 size_t optim_workspace_bytes();
 // sq_a / sq_c: per-network sum-of-squares slots already produced by the backward-w epilogues (n_sq_* > 0), or
 // null -> a norm pass over the (all-reduced) gradients is run first.

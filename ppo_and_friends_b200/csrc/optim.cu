@@ -37,7 +37,9 @@ adam_update_kernel(float* __restrict__ params, const float* __restrict__ grads, 
                    int n_sq_a, const double* __restrict__ sq_c, int n_sq_c, const double* __restrict__ hp,
                    int64_t* __restrict__ adam_step, int32_t* __restrict__ mb_cursor, unsigned int* __restrict__ ticket) {
     __shared__ double s_scr[32];
+    __shared__ double s_pw[2];
     __shared__ float s_coef[2];
+    double* pw = reinterpret_cast<double*>(ticket + 2);   // cached (t, beta1^t, beta2^t)
     // ---- fold the sum-of-squares slots (same order in every CTA -> identical scalars everywhere) ----
     double ta = 0.0, tc = 0.0;
     for (int k = threadIdx.x; k < n_sq_a; k += blockDim.x) ta += sq_a[k];
@@ -60,8 +62,11 @@ adam_update_kernel(float* __restrict__ params, const float* __restrict__ grads, 
     __shared__ float s_f[6];
     if (threadIdx.x == 0) {
         const double b1d = hp[PPOAF_HP_BETA1], b2d = hp[PPOAF_HP_BETA2];
-        const double bc1 = 1.0 - pow(b1d, double(t));
-        const double bc2 = 1.0 - pow(b2d, double(t));
+        double p1, p2;
+        beta_powers(pw, t, b1d, b2d, p1, p2);
+        s_pw[0] = p1; s_pw[1] = p2;
+        const double bc1 = 1.0 - p1;
+        const double bc2 = 1.0 - p2;
         s_f[0] = float(-(hp[PPOAF_HP_LR] / bc1));     // -step_size = -lr / (1 - beta1^t)
         s_f[1] = float(sqrt(bc2));                    // sqrt(1 - beta2^t)
         s_f[2] = float(1.0 - b1d);
@@ -104,6 +109,7 @@ adam_update_kernel(float* __restrict__ params, const float* __restrict__ grads, 
         if (atomicAdd(ticket, 1u) == gridDim.x - 1) {
             *adam_step = t;
             if (mb_cursor) *mb_cursor += 1;
+            pw[0] = double(t); pw[1] = s_pw[0]; pw[2] = s_pw[1];
             *ticket = 0u;
         }
     }

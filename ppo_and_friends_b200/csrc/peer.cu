@@ -18,10 +18,17 @@
 
 namespace ppoaf {
 
-constexpr int kPeerThreads = 256;
+constexpr int kPeerThreads = 1024;
 constexpr int kPeerMaxRanks = 8;
-constexpr int kPeerMaxVec = 8;            // float4 slots per thread held in registers
+constexpr int kPeerMaxVec = 2;            // float4 slots per thread held in registers (1 for a 460 K-parameter policy)
 constexpr long long kSpinLimit = 4000000000LL;   // ~2 s of SM clock
+
+#ifdef PPOAF_PEER_TIMING
+__device__ long long g_peer_stamps[16];
+#define PEER_STAMP(k) do { if (blockIdx.x == 0 && threadIdx.x == 0) g_peer_stamps[k] = clock64(); } while (0)
+#else
+#define PEER_STAMP(k) do {} while (0)
+#endif
 
 struct PeerArgs {
     const float* peer_grads[kPeerMaxRanks];   // gradient buffer of every rank for THIS parity (index = rank)
@@ -52,10 +59,13 @@ peer_allreduce_adam_kernel(const PeerArgs pa, float* __restrict__ params, float*
                            int64_t* __restrict__ adam_step, int32_t* __restrict__ mb_cursor,
                            double* __restrict__ partials, uint32_t* __restrict__ ctrl) {
     __shared__ double s_scr[32];
+    __shared__ double s_pw[2];
     __shared__ float s_f[8];
     __shared__ int s_err;
     const int tid = threadIdx.x;
     const int R = pa.n_ranks;
+    double* pw = reinterpret_cast<double*>(ctrl + 8);   // cached (t, beta1^t, beta2^t)
+    PEER_STAMP(0);
     const uint32_t epoch = ctrl[0] + 1;        // every CTA reads the value of the previous call (updated at the very end)
     if (tid == 0) s_err = 0;
 
@@ -76,6 +86,7 @@ peer_allreduce_adam_kernel(const PeerArgs pa, float* __restrict__ params, float*
         return;
     }
 
+    PEER_STAMP(1);
     // ---- 2. one-shot reduce in rank order, gradient kept in registers ----
     const int64_t nv = n_total / 4, na = n_actor / 4;
     const int64_t stride = int64_t(gridDim.x) * blockDim.x;
@@ -86,18 +97,23 @@ peer_allreduce_adam_kernel(const PeerArgs pa, float* __restrict__ params, float*
         const int64_t i = int64_t(blockIdx.x) * blockDim.x + tid + k * stride;
         g[k] = make_float4(0.f, 0.f, 0.f, 0.f);
         if (i < nv) {
-            float4 acc = reinterpret_cast<const float4*>(pa.peer_grads[0])[i];
-            for (int r = 1; r < R; ++r) {
-                const float4 x = reinterpret_cast<const float4*>(pa.peer_grads[r])[i];
-                acc.x += x.x; acc.y += x.y; acc.z += x.z; acc.w += x.w;
-            }
+            float4 x[kPeerMaxRanks];               // all R loads (local + NVLink) are issued before any is consumed
+#pragma unroll
+            for (int r = 0; r < kPeerMaxRanks; ++r)
+                if (r < R) x[r] = reinterpret_cast<const float4*>(pa.peer_grads[r])[i];
+            float4 acc = x[0];
+#pragma unroll
+            for (int r = 1; r < kPeerMaxRanks; ++r)
+                if (r < R) { acc.x += x[r].x; acc.y += x[r].y; acc.z += x[r].z; acc.w += x[r].w; }
             g[k] = acc;
             const float q = fmaf(acc.x, acc.x, fmaf(acc.y, acc.y, fmaf(acc.z, acc.z, acc.w * acc.w)));
             if (i < na) sa += double(q); else sc += double(q);
         }
     }
+    PEER_STAMP(2);
     sa = block_sum(sa, s_scr);
     sc = block_sum(sc, s_scr);
+    PEER_STAMP(3);
 
     // ---- 3. local grid barrier + fixed-order fold of the CTA partials ----
     if (tid == 0) {
@@ -121,11 +137,13 @@ peer_allreduce_adam_kernel(const PeerArgs pa, float* __restrict__ params, float*
         if (tid == 0) atomicExch(ctrl + 4, 2u);
         return;
     }
+    PEER_STAMP(4);
     double ta = 0.0, tc = 0.0;
     for (int b = tid; b < int(gridDim.x); b += blockDim.x) { ta += __ldcg(&partials[2 * b]); tc += __ldcg(&partials[2 * b + 1]); }
     ta = block_sum(ta, s_scr);
     tc = block_sum(tc, s_scr);
 
+    PEER_STAMP(5);
     // ---- 4. scalars, then Adam on the register-held gradient ----
     const int64_t t = *adam_step + 1;
     if (tid == 0) {
@@ -137,8 +155,11 @@ peer_allreduce_adam_kernel(const PeerArgs pa, float* __restrict__ params, float*
             cc = fminf(max_norm / (float(sqrt(tc) * double(inv_world)) + 1e-6f), 1.f);
         }
         const double b1d = hp[PPOAF_HP_BETA1], b2d = hp[PPOAF_HP_BETA2];
-        s_f[0] = float(-(hp[PPOAF_HP_LR] / (1.0 - pow(b1d, double(t)))));
-        s_f[1] = float(sqrt(1.0 - pow(b2d, double(t))));
+        double p1, p2;
+        beta_powers(pw, t, b1d, b2d, p1, p2);
+        s_pw[0] = p1; s_pw[1] = p2;
+        s_f[0] = float(-(hp[PPOAF_HP_LR] / (1.0 - p1)));
+        s_f[1] = float(sqrt(1.0 - p2));
         s_f[2] = float(1.0 - b1d);
         s_f[3] = float(b2d);
         s_f[4] = float(1.0 - b2d);
@@ -147,6 +168,7 @@ peer_allreduce_adam_kernel(const PeerArgs pa, float* __restrict__ params, float*
         s_f[7] = cc;
     }
     __syncthreads();
+    PEER_STAMP(6);
     const float neg_step_size = s_f[0], bc2_sqrt = s_f[1], w1 = s_f[2], beta2 = s_f[3], w2 = s_f[4], eps = s_f[5];
     const float inv_world = float(hp[PPOAF_HP_INV_WORLD]);
     float4* p4 = reinterpret_cast<float4*>(params);
@@ -172,6 +194,7 @@ peer_allreduce_adam_kernel(const PeerArgs pa, float* __restrict__ params, float*
         m4[i] = make_float4(mm[0], mm[1], mm[2], mm[3]);
         v4[i] = make_float4(vv[0], vv[1], vv[2], vv[3]);
     }
+    PEER_STAMP(7);
     // ---- the last CTA to finish advances the counters (everyone has read adam_step / ctrl[0] by then) ----
     __syncthreads();
     if (tid == 0) {
@@ -179,6 +202,7 @@ peer_allreduce_adam_kernel(const PeerArgs pa, float* __restrict__ params, float*
         if (atomicAdd(ctrl + 3, 1u) == gridDim.x - 1) {
             *adam_step = t;
             if (mb_cursor) *mb_cursor += 1;
+            pw[0] = double(t); pw[1] = s_pw[0]; pw[2] = s_pw[1];
             ctrl[0] = epoch;
             ctrl[3] = 0u;
         }
@@ -257,3 +281,9 @@ extern "C" int ppoaf_peer_allreduce_adam(const void* const* peer_grads, void* co
     PPOAF_CHECK_LAUNCH("peer_allreduce_adam_kernel");
     return 0;
 }
+
+#ifdef PPOAF_PEER_TIMING
+extern "C" int ppoaf_debug_peer_stamps(long long* out_host) {
+    return cudaMemcpyFromSymbol(out_host, ppoaf::g_peer_stamps, sizeof(long long) * 16) == cudaSuccess ? 0 : 1;
+}
+#endif
