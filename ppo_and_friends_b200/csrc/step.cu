@@ -148,7 +148,17 @@ extern "C" size_t ppoaf_update_workspace_bytes(const ppoaf_update_cfg* cfg, int3
         }                                                                              \
     } while (0)
 
+#ifdef PPOAF_GEMM_TIMING
+// debug build only: stop the chain after PPOAF_STOP_AFTER launches (prefix timing of the step, scratch/prefix_times.py)
+#include <stdlib.h>
+static int stop_after() { const char* e = getenv("PPOAF_STOP_AFTER"); return e ? atoi(e) : 1000; }
+#define PPOAF_STEP_LIMIT() do { if (++launched__ > stop_after()) return 0; } while (0)
+#else
+#define PPOAF_STEP_LIMIT() do {} while (0)
+#endif
+
 extern "C" int ppoaf_ppo_minibatch_grads(const ppoaf_update_cfg* cfg, const ppoaf_update_bufs* b, void* stream) {
+    int launched__ = 0; (void)launched__;
     if (check_cfg(cfg, "ppoaf_ppo_minibatch_grads")) return 1;
     PPOAF_CHECK_ARG(b != nullptr && b->batch >= 1 && b->batch <= b->batch_size && b->n_flat > 0,
                     "ppoaf_ppo_minibatch_grads: bad batch sizes");
@@ -184,6 +194,7 @@ extern "C" int ppoaf_ppo_minibatch_grads(const ppoaf_update_cfg* cfg, const ppoa
                             par[k] + off[k][2 * l], par[k] + off[k][2 * l + 1], ns[k]->act[l + 1], rows,
                             net[k]->dims[l], net[k]->dims[l + 1], last ? PPOAF_ACT_IDENTITY : net[k]->activation);
         }
+        PPOAF_STEP_LIMIT();
         if (grp.launch(b->mb_cursor, b->batch_size, s)) return 2;
     }
 
@@ -219,6 +230,7 @@ extern "C" int ppoaf_ppo_minibatch_grads(const ppoaf_update_cfg* cfg, const ppoa
     a.normalize_values = cfg->normalize_values;
     a.vf_clip_enabled = cfg->vf_clip_enabled;
     a.min_std = cfg->min_std;
+    PPOAF_STEP_LIMIT();
     if (launch_ppo_loss(a, s)) return 2;
 
     // ---- backward: dW/db and dX of one layer of both networks per grouped launch, top layer first ----
@@ -238,6 +250,7 @@ extern "C" int ppoaf_ppo_minibatch_grads(const ppoaf_update_cfg* cfg, const ppoa
                 grp.add_backward_x(ns[k]->dz[l + 1], par[k] + off[k][2 * l], ns[k]->act[l], ns[k]->dz[l], rows,
                                    net[k]->dims[l], net[k]->dims[l + 1], net[k]->activation);
         }
+        PPOAF_STEP_LIMIT();
         if (grp.launch(b->mb_cursor, b->batch_size, s)) return 2;
     }
     return 0;
