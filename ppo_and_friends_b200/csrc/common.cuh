@@ -111,4 +111,34 @@ __device__ __forceinline__ Moments shfl_xor_moments(const Moments& m, int o) {
     return r;
 }
 
+__device__ __forceinline__ float fast_tanh(float x) {
+    // tanh(x) = 1 - 2 / (exp(2x) + 1); ex2/rcp based, absolute error ~2e-7 (the epilogues' hot math)
+    const float t = __expf(2.f * x);
+    return 1.f - __fdividef(2.f, t + 1.f);
+}
+__device__ __forceinline__ void act_fwd4(float (&o)[4], int act) {
+    if (act == PPOAF_ACT_TANH) {
+#pragma unroll
+        for (int j = 0; j < 4; ++j) o[j] = fast_tanh(o[j]);
+    } else if (act == PPOAF_ACT_RELU) {
+#pragma unroll
+        for (int j = 0; j < 4; ++j) o[j] = o[j] > 0.f ? o[j] : 0.f;
+    } else if (act == PPOAF_ACT_LEAKY_RELU) {
+#pragma unroll
+        for (int j = 0; j < 4; ++j) o[j] = o[j] > 0.f ? o[j] : 0.01f * o[j];
+    }
+}
+__device__ __forceinline__ void act_bwd4(float (&o)[4], const float (&y)[4], int act) {
+    if (act == PPOAF_ACT_TANH) {
+#pragma unroll
+        for (int j = 0; j < 4; ++j) o[j] *= 1.f - y[j] * y[j];
+    } else if (act == PPOAF_ACT_RELU) {
+#pragma unroll
+        for (int j = 0; j < 4; ++j) o[j] = y[j] > 0.f ? o[j] : 0.f;
+    } else if (act == PPOAF_ACT_LEAKY_RELU) {
+#pragma unroll
+        for (int j = 0; j < 4; ++j) o[j] = y[j] > 0.f ? o[j] : 0.01f * o[j];
+    }
+}
+
 }  // namespace ppoaf

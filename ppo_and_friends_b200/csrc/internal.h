@@ -59,7 +59,24 @@ struct LossArgs {
     int head, act_dim, pred_dim;
     int use_huber, normalize_adv, normalize_values, vf_clip_enabled;
     float min_std;
+    // fused head layers (loss_head_fusable): the last Linear of both networks and its dX are computed by the loss
+    // kernel itself, so actor_out / critic_out are not read and two GEMM launches disappear from the step
+    int fused;
+    const float* h_actor;        // [batch, Ha] activations below the actor head
+    const float* h_critic;       // [batch, Hc]
+    const float* W_actor;        // [pred, Ha]
+    const float* b_actor;        // [pred]
+    const float* W_critic;       // [1, Hc]
+    const float* b_critic;       // [1]
+    float* dz_actor;             // [batch, Ha]  dL/d(pre-activation of the layer below the head)
+    float* dz_critic;            // [batch, Hc]
+    int Ha, Hc, act;
+    // optional L2 prefetch of the next minibatch's gathered rows (obs, critic obs); pf_rows[0] == null: off
+    const void* pf_rows[2];
+    int pf_row_bytes[2];
+    int64_t n_flat;
 };
+bool loss_head_fusable(int pred_dim, int Ha, int Hc, int vf_clip_enabled);
 size_t loss_workspace_bytes(int max_batch, int act_dim);
 int launch_ppo_loss(const LossArgs& a, cudaStream_t s);
 

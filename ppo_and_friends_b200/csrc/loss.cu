@@ -13,12 +13,22 @@
 namespace ppoaf {
 
 constexpr int kMaxAct = 64;
-constexpr int kG = 8;                       // lanes that share one sample (each owns dims l, l+8, ...)
-constexpr int kPerLane = kMaxAct / kG;      // 8
-constexpr int kLossThreads = 256;           // 32 samples per CTA
+constexpr int kG = 32;                      // lanes that share one sample: one warp (each lane owns dims l, l+32)
+constexpr int kPerLane = kMaxAct / kG;      // 2
+constexpr int kLossThreads = 256;           // 8 samples per CTA
 constexpr int kSamplesPerBlock = kLossThreads / kG;
 enum { LS_ACTOR = 0, LS_CRITIC, LS_CRITIC_CLIPPED, LS_ENTROPY, LS_KL, LS_BAD_RATIO, LS_BAD_VALUE, kLossScalars };
 constexpr int kPartialStride = kLossScalars + kMaxAct;
+
+// fused head layers: widths the register-resident path supports
+constexpr int kFusedMaxPred = 24;           // actor head outputs
+constexpr int kFusedMaxChunks = 2;          // hidden width <= 256: lane gl owns columns 4 (gl + 32 c) .. + 3
+constexpr int kFusedPredLd = kFusedMaxPred + 1;
+
+bool loss_head_fusable(int pred_dim, int Ha, int Hc, int vf_clip_enabled) {
+    auto ok = [](int H) { return H % 4 == 0 && H >= 4 && H <= 4 * kG * kFusedMaxChunks; };
+    return pred_dim <= kFusedMaxPred && ok(Ha) && ok(Hc) && !vf_clip_enabled;
+}
 
 constexpr float kLogSqrt2Pi = 0.91893853320467274178f;
 constexpr float kCatEps = 1.1920928955078125e-07f;   // torch.finfo(float32).eps
@@ -49,7 +59,9 @@ __device__ __forceinline__ float group_max(float v) {
     return v;
 }
 
+template <bool FUSED>
 __global__ void __launch_bounds__(kLossThreads) ppo_loss_kernel(const LossArgs a) {
+    extern __shared__ __align__(16) float s_dyn[];      // FUSED: W_actor [pred][Ha+4] | W_critic [Hc] | biases | pred | dpred
     __shared__ float s_sd[kMaxAct], s_dsd[kMaxAct];
     __shared__ double s_red[kLossThreads / 32][kPartialStride];
     __shared__ double s_tot[kPartialStride];
@@ -75,6 +87,54 @@ __global__ void __launch_bounds__(kLossThreads) ppo_loss_kernel(const LossArgs a
         const float sig = ls > 20.f ? 1.f : 1.f / (1.f + expf(-ls));
         s_dsd[tid] = sp > a.min_std ? sig : (sp == a.min_std ? 0.5f * sig : 0.f);
     }
+    // ---- all global loads of the sample are issued before the staging barrier (one L2 round trip, not three) ----
+    const int64_t j = live ? idx[i] : 0;
+    const int smp = tid / kG;                                        // sample slot inside the CTA
+    float4 ha[kFusedMaxChunks], hc[kFusedMaxChunks];
+    if constexpr (FUSED) {
+        const float* hra = a.h_actor + int64_t(live ? i : 0) * a.Ha + 4 * gl;
+        const float* hrc = a.h_critic + int64_t(live ? i : 0) * a.Hc + 4 * gl;
+#pragma unroll
+        for (int c = 0; c < kFusedMaxChunks; ++c) {
+            const int col = 4 * (gl + kG * c);
+            ha[c] = (col < a.Ha && live) ? *reinterpret_cast<const float4*>(hra + 4 * kG * c) : make_float4(0.f, 0.f, 0.f, 0.f);
+            hc[c] = (col < a.Hc && live) ? *reinterpret_cast<const float4*>(hrc + 4 * kG * c) : make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+    }
+    float adv = live ? a.advantages[j] : 0.f;
+    const float lp_old = live ? a.log_probs[j] : 0.f;
+    float target = live ? a.rewards_to_go[j] : 0.f;
+    if (a.pf_rows[0] && live) {
+        // pull the NEXT minibatch's observation rows into L2 while this step's backward pass runs: the first-layer
+        // GEMMs of the next step then gather from L2 instead of HBM
+        const int64_t nxt = int64_t(cur + 1) * a.batch_size + i;
+        if (nxt < a.n_flat) {
+            const int64_t jn = a.perm[nxt];
+            const char* r0 = reinterpret_cast<const char*>(a.pf_rows[0]) + jn * a.pf_row_bytes[0];
+            const char* r1 = reinterpret_cast<const char*>(a.pf_rows[1]) + jn * a.pf_row_bytes[1];
+            for (int o = gl * 128; o < a.pf_row_bytes[0]; o += kG * 128) asm volatile("prefetch.global.L2 [%0];" ::"l"(r0 + o));
+            for (int o = gl * 128; o < a.pf_row_bytes[1]; o += kG * 128) asm volatile("prefetch.global.L2 [%0];" ::"l"(r1 + o));
+        }
+    }
+
+    // ---- fused heads: stage the two head layers' weights (coalesced 16-byte loads) ----
+    const int ldw = a.Ha + 4;                                        // rows of W_actor land on distinct bank groups
+    float* s_wa = s_dyn;
+    float* s_wc = s_wa + a.pred_dim * ldw;
+    float* s_b = s_wc + a.Hc;                                        // [pred + 1]
+    float* s_pred = s_b + ((a.pred_dim + 1 + 3) & ~3);               // [samples per block][kFusedPredLd]
+    float* s_dpred = s_pred + kSamplesPerBlock * kFusedPredLd;
+    if constexpr (FUSED) {
+        const int qa = a.Ha / 4;
+        for (int t = tid; t < a.pred_dim * qa; t += kLossThreads) {
+            const int row = t / qa, c4 = t - row * qa;
+            *reinterpret_cast<float4*>(s_wa + row * ldw + 4 * c4) = *reinterpret_cast<const float4*>(a.W_actor + int64_t(row) * a.Ha + 4 * c4);
+        }
+        for (int t = tid; t < a.Hc / 4; t += kLossThreads)
+            *reinterpret_cast<float4*>(s_wc + 4 * t) = *reinterpret_cast<const float4*>(a.W_critic + 4 * t);
+        if (tid < a.pred_dim) s_b[tid] = a.b_actor[tid];
+        if (tid == 0) s_b[a.pred_dim] = a.b_critic[0];
+    }
     __syncthreads();
 
     float sc[kLossScalars];
@@ -84,19 +144,50 @@ __global__ void __launch_bounds__(kLossThreads) ppo_loss_kernel(const LossArgs a
 #pragma unroll
     for (int k = 0; k < kPerLane; ++k) dsd[k] = 0.f;
 
-    // every lane of the group runs the (cheap) per-sample scalar math so the shuffles stay convergent
-    const int64_t j = live ? idx[i] : 0;
-    float adv = live ? a.advantages[j] : 0.f;
     if (a.normalize_adv) adv = (adv - a.mb_adv_stats[2 * cur]) / a.mb_adv_stats[2 * cur + 1];
-    const float lp_old = live ? a.log_probs[j] : 0.f;
-    float target = live ? a.rewards_to_go[j] : 0.f;
     if (a.normalize_values) target = (target - a.mb_val_stats[2 * cur]) / a.mb_val_stats[2 * cur + 1];
-    const float v = live ? a.critic_out[i] : 0.f;
+    // ---- fused heads, forward: every lane dots its columns of the hidden activations with all head rows, the 8
+    // lanes of the sample fold their partial sums, and the outputs go to shared memory ----
+    float v_fused = 0.f;
+    if constexpr (FUSED) {
+        float acc[kFusedMaxPred];
+#pragma unroll
+        for (int d = 0; d < kFusedMaxPred; ++d) acc[d] = 0.f;
+#pragma unroll
+        for (int c = 0; c < kFusedMaxChunks; ++c) {
+            const int col = 4 * (gl + kG * c);
+            if (col < a.Ha) {
+                const float* wcol = s_wa + col;
+#pragma unroll
+                for (int d = 0; d < kFusedMaxPred; ++d) {
+                    if (d < a.pred_dim) {
+                        const float4 w = *reinterpret_cast<const float4*>(wcol + d * ldw);
+                        acc[d] = fmaf(ha[c].x, w.x, fmaf(ha[c].y, w.y, fmaf(ha[c].z, w.z, fmaf(ha[c].w, w.w, acc[d]))));
+                    }
+                }
+            }
+            if (col < a.Hc) {
+                const float4 w = *reinterpret_cast<const float4*>(s_wc + col);
+                v_fused = fmaf(hc[c].x, w.x, fmaf(hc[c].y, w.y, fmaf(hc[c].z, w.z, fmaf(hc[c].w, w.w, v_fused))));
+            }
+        }
+        v_fused = group_sum(v_fused) + s_b[a.pred_dim];
+#pragma unroll
+        for (int d = 0; d < kFusedMaxPred; ++d) {
+            if (d < a.pred_dim) {
+                const float t = group_sum(acc[d]);
+                if ((d & (kG - 1)) == gl) s_pred[smp * kFusedPredLd + d] = t + s_b[d];
+            }
+        }
+        __syncwarp();                                                // the lanes of a sample share one warp
+    }
+    const float v = FUSED ? (live ? v_fused : 0.f) : (live ? a.critic_out[i] : 0.f);
     if (live && gl == 0) a.values[j] = v;                            // dataset.values[batch_idxs] = values (ppo.py:2340)
     float bad_value = isnan(v) ? 1.f : 0.f;
 
-    const float* pred = a.actor_out + int64_t(live ? i : 0) * a.pred_dim;
+    const float* pred = FUSED ? s_pred + smp * kFusedPredLd : a.actor_out + int64_t(live ? i : 0) * a.pred_dim;
     float* dpred = a.d_actor_out + int64_t(live ? i : 0) * a.pred_dim;
+    float* sdp = s_dpred + smp * kFusedPredLd;                       // FUSED: dL/d(actor out) kept for the head's dX
     float lp = 0.f, ent = 0.f;
 
     if (gaussian) {
@@ -146,7 +237,9 @@ __global__ void __launch_bounds__(kLossThreads) ppo_loss_kernel(const LossArgs a
                 const float sd = s_sd[d], var = sd * sd;
                 const float tmask = (1.f - thm[k] * thm[k] >= 1e-6f) ? 1.f : 0.f;
                 // dlp/dmu = z/var ; dH/dmu = -2 tanh(mu)
-                dpred[d] = g_lp * on[k] * (z[k] / var) + g_ent * tmask * (-2.f * thm[k]);
+                const float gd = g_lp * on[k] * (z[k] / var) + g_ent * tmask * (-2.f * thm[k]);
+                dpred[d] = gd;
+                if constexpr (FUSED) sdp[d] = gd;
                 // dlp/dsd = z^2/sd^3 - 1/sd ; dH/dsd = 1/sd
                 dsd[k] = g_lp * on[k] * ((z[k] * z[k]) / (var * sd) - 1.f / sd) + g_ent * one[k] * (1.f / sd);
             }
@@ -222,14 +315,19 @@ __global__ void __launch_bounds__(kLossThreads) ppo_loss_kernel(const LossArgs a
 #pragma unroll
         for (int k = 0; k < kPerLane; ++k) {
             const int c = gl + k * kG;
-            if (c < n && live) dpred[c] = p[k] * (G[k] - dpdotp);
+            if (c < n && live) {
+                const float gd = p[k] * (G[k] - dpdotp);
+                dpred[c] = gd;
+                if constexpr (FUSED) sdp[c] = gd;
+            }
         }
     }
 
     // ---------------- critic ----------------
+    float dv1 = 0.f;
+    if (FUSED || (gl == 0 && live)) sc[LS_CRITIC] = critic_term(v, target, a.use_huber, dv1);
+    if (FUSED && !(gl == 0 && live)) sc[LS_CRITIC] = 0.f;
     if (gl == 0 && live) {
-        float dv1;
-        sc[LS_CRITIC] = critic_term(v, target, a.use_huber, dv1);
         if (a.vf_clip_enabled) {
             const float vc = fminf(fmaxf(v, -vf_clip), vf_clip);
             float dv2;
@@ -244,6 +342,43 @@ __global__ void __launch_bounds__(kLossThreads) ppo_loss_kernel(const LossArgs a
     const float bad_any = group_max(bad_value);
     sc[LS_BAD_VALUE] = (live && gl == 0) ? bad_any : 0.f;
 
+    // ---- fused heads, backward: dX of the two head layers times the activation derivative of the layer below ----
+    if constexpr (FUSED) {
+        __syncwarp();
+        float dp[kFusedMaxPred];
+#pragma unroll
+        for (int d = 0; d < kFusedMaxPred; ++d) dp[d] = (d < a.pred_dim && live) ? sdp[d] : 0.f;
+        const float gv = live ? dv1 * inv_b : 0.f;
+        float* dza = a.dz_actor + int64_t(live ? i : 0) * a.Ha + 4 * gl;
+        float* dzc = a.dz_critic + int64_t(live ? i : 0) * a.Hc + 4 * gl;
+#pragma unroll
+        for (int c = 0; c < kFusedMaxChunks; ++c) {
+            const int col = 4 * (gl + kG * c);
+            if (col < a.Ha) {
+                const float* wcol = s_wa + col;
+                float t[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+                for (int d = 0; d < kFusedMaxPred; ++d) {
+                    if (d < a.pred_dim) {
+                        const float4 w = *reinterpret_cast<const float4*>(wcol + d * ldw);
+                        t[0] = fmaf(dp[d], w.x, t[0]); t[1] = fmaf(dp[d], w.y, t[1]);
+                        t[2] = fmaf(dp[d], w.z, t[2]); t[3] = fmaf(dp[d], w.w, t[3]);
+                    }
+                }
+                const float y[4] = {ha[c].x, ha[c].y, ha[c].z, ha[c].w};
+                act_bwd4(t, y, a.act);
+                if (live) *reinterpret_cast<float4*>(dza + 4 * kG * c) = make_float4(t[0], t[1], t[2], t[3]);
+            }
+            if (col < a.Hc) {
+                const float4 w = *reinterpret_cast<const float4*>(s_wc + col);
+                float t[4] = {gv * w.x, gv * w.y, gv * w.z, gv * w.w};
+                const float y[4] = {hc[c].x, hc[c].y, hc[c].z, hc[c].w};
+                act_bwd4(t, y, a.act);
+                if (live) *reinterpret_cast<float4*>(dzc + 4 * kG * c) = make_float4(t[0], t[1], t[2], t[3]);
+            }
+        }
+    }
+
     // ---------------- CTA reduction (fp64, fixed order) ----------------
     const int n_extra = gaussian ? a.act_dim : 0;
 #pragma unroll
@@ -254,9 +389,9 @@ __global__ void __launch_bounds__(kLossThreads) ppo_loss_kernel(const LossArgs a
     if (gaussian) {
 #pragma unroll
         for (int k = 0; k < kPerLane; ++k) {
-            double w = double(dsd[k]);                   // sum the 4 sample-groups of the warp: lanes l, l+8, l+16, l+24
-            w += __shfl_xor_sync(kFull, w, 8);
-            w += __shfl_xor_sync(kFull, w, 16);
+            double w = double(dsd[k]);                   // sum over the sample-groups that share the warp
+#pragma unroll
+            for (int o = kG; o < 32; o <<= 1) w += __shfl_xor_sync(kFull, w, o);
             if (lane < kG) s_red[warp][kLossScalars + lane + k * kG] = w;
         }
     }
@@ -341,7 +476,14 @@ int launch_ppo_loss(const LossArgs& a, cudaStream_t s) {
                     "ppo loss: act_dim / prediction width must be in [1, %d]", kMaxAct);
     PPOAF_CHECK_ARG(a.batch >= 2, "ppo loss: minibatches of fewer than 2 rows are skipped by the caller");
     const int blocks = (a.batch + kSamplesPerBlock - 1) / kSamplesPerBlock;
-    ppo_loss_kernel<<<blocks, kLossThreads, 0, s>>>(a);
+    if (a.fused) {
+        PPOAF_CHECK_ARG(loss_head_fusable(a.pred_dim, a.Ha, a.Hc, a.vf_clip_enabled), "ppo loss: head layers are not fusable");
+        const size_t smem = sizeof(float) * size_t(a.pred_dim * (a.Ha + 4) + a.Hc + ((a.pred_dim + 1 + 3) & ~3) +
+                                                   2 * kSamplesPerBlock * kFusedPredLd);
+        ppo_loss_kernel<true><<<blocks, kLossThreads, smem, s>>>(a);
+    } else {
+        ppo_loss_kernel<false><<<blocks, kLossThreads, 0, s>>>(a);
+    }
     PPOAF_CHECK_LAUNCH("ppo_loss_kernel");
     if (a.vf_clip_enabled) {
         const float* wsel = reinterpret_cast<const float*>(reinterpret_cast<const double*>(a.partials) +

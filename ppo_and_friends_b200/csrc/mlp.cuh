@@ -47,7 +47,7 @@ __device__ __forceinline__ float act_bwd_from_out(float y, int act) {
 }
 
 enum { EPI_FWD = 0, EPI_BWD_X = 1, EPI_BWD_W = 2 };
-constexpr int kMaxGroup = 4;
+constexpr int kMaxGroup = 6;
 
 struct GemmProblem {
     const float* A; const float* B; float* C;
@@ -181,42 +181,12 @@ __device__ __forceinline__ void stage_oc(float* panel, const float* __restrict__
     }
 }
 
-__device__ __forceinline__ float fast_tanh(float x) {
-    // tanh(x) = 1 - 2 / (exp(2x) + 1); ex2/rcp based, absolute error ~2e-7 (the epilogues' hot math)
-    const float t = __expf(2.f * x);
-    return 1.f - __fdividef(2.f, t + 1.f);
-}
 __device__ __forceinline__ float act_fwd_fast(float x, int act) {
     switch (act) {
         case PPOAF_ACT_RELU: return x > 0.f ? x : 0.f;
         case PPOAF_ACT_LEAKY_RELU: return x > 0.f ? x : 0.01f * x;
         case PPOAF_ACT_TANH: return fast_tanh(x);
         default: return x;
-    }
-}
-
-__device__ __forceinline__ void act_fwd4(float (&o)[4], int act) {
-    if (act == PPOAF_ACT_TANH) {
-#pragma unroll
-        for (int j = 0; j < 4; ++j) o[j] = fast_tanh(o[j]);
-    } else if (act == PPOAF_ACT_RELU) {
-#pragma unroll
-        for (int j = 0; j < 4; ++j) o[j] = o[j] > 0.f ? o[j] : 0.f;
-    } else if (act == PPOAF_ACT_LEAKY_RELU) {
-#pragma unroll
-        for (int j = 0; j < 4; ++j) o[j] = o[j] > 0.f ? o[j] : 0.01f * o[j];
-    }
-}
-__device__ __forceinline__ void act_bwd4(float (&o)[4], const float (&y)[4], int act) {
-    if (act == PPOAF_ACT_TANH) {
-#pragma unroll
-        for (int j = 0; j < 4; ++j) o[j] *= 1.f - y[j] * y[j];
-    } else if (act == PPOAF_ACT_RELU) {
-#pragma unroll
-        for (int j = 0; j < 4; ++j) o[j] = y[j] > 0.f ? o[j] : 0.f;
-    } else if (act == PPOAF_ACT_LEAKY_RELU) {
-#pragma unroll
-        for (int j = 0; j < 4; ++j) o[j] = y[j] > 0.f ? o[j] : 0.01f * o[j];
     }
 }
 

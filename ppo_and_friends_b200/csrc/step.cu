@@ -10,6 +10,7 @@
 #include <stdarg.h>
 
 #include "internal.h"
+#include <stdlib.h>
 
 namespace ppoaf {
 
@@ -183,9 +184,15 @@ extern "C" int ppoaf_ppo_minibatch_grads(const ppoaf_update_cfg* cfg, const ppoa
     const int L[2] = {cfg->actor.n_layers, cfg->critic.n_layers};
     const int Lmax = L[0] > L[1] ? L[0] : L[1];
     const int rows = b->batch;
+    // The two head layers (last Linear of actor and critic) and their dX are computed inside the loss kernel when
+    // their shapes allow it: two of the ten launches of the step disappear.
+    const bool fuse_heads = L[0] == L[1] && L[0] >= 2 && cfg->actor.activation == cfg->critic.activation &&
+                            getenv("PPOAF_NO_HEAD_FUSION") == nullptr &&
+                            loss_head_fusable(cfg->actor.dims[L[0]], cfg->actor.dims[L[0] - 1],
+                                              cfg->critic.dims[L[1] - 1], cfg->vf_clip_enabled);
 
     // ---- forward: layer l of both networks in one grouped launch ----
-    for (int l = 0; l < Lmax; ++l) {
+    for (int l = 0; l < Lmax - (fuse_heads ? 1 : 0); ++l) {
         GemmGroup grp(gemm_backend());
         for (int k = 0; k < 2; ++k) {
             if (l >= L[k]) continue;
@@ -230,18 +237,43 @@ extern "C" int ppoaf_ppo_minibatch_grads(const ppoaf_update_cfg* cfg, const ppoa
     a.normalize_values = cfg->normalize_values;
     a.vf_clip_enabled = cfg->vf_clip_enabled;
     a.min_std = cfg->min_std;
+    a.pf_rows[0] = b->obs;
+    a.pf_rows[1] = b->critic_obs;
+    a.pf_row_bytes[0] = cfg->actor.dims[0] * int(sizeof(float));
+    a.pf_row_bytes[1] = cfg->critic.dims[0] * int(sizeof(float));
+    a.n_flat = b->n_flat;
+    a.fused = fuse_heads ? 1 : 0;
+    if (fuse_heads) {
+        a.h_actor = sc.actor.act[L[0] - 1];
+        a.h_critic = sc.critic.act[L[1] - 1];
+        a.W_actor = par[0] + off[0][2 * (L[0] - 1)];
+        a.b_actor = par[0] + off[0][2 * (L[0] - 1) + 1];
+        a.W_critic = par[1] + off[1][2 * (L[1] - 1)];
+        a.b_critic = par[1] + off[1][2 * (L[1] - 1) + 1];
+        a.dz_actor = sc.actor.dz[L[0] - 1];
+        a.dz_critic = sc.critic.dz[L[1] - 1];
+        a.Ha = cfg->actor.dims[L[0] - 1];
+        a.Hc = cfg->critic.dims[L[1] - 1];
+        a.act = cfg->actor.activation;
+    }
     PPOAF_STEP_LIMIT();
     if (launch_ppo_loss(a, s)) return 2;
 
     // ---- backward: dW/db and dX of one layer of both networks per grouped launch, top layer first ----
     double* sq[2] = {sc.sq_actor, sc.sq_critic};
     int sq_used[2] = {0, 0};
-    for (int k_top = 0; k_top < Lmax; ++k_top) {
+    for (int k_top = fuse_heads ? 1 : 0; k_top < Lmax; ++k_top) {
         GemmGroup grp(gemm_backend());
         for (int k = 0; k < 2; ++k) {
             const int l = L[k] - 1 - k_top;
             if (l < 0) continue;
             const bool first = l == 0;
+            if (fuse_heads && k_top == 1) {    // the heads' dW / db (their dX came out of the loss kernel)
+                const int lh = L[k] - 1;
+                sq_used[k] += grp.add_backward_w(ns[k]->dz[lh + 1], ns[k]->act[lh], net[k]->dims[lh], nullptr,
+                                                 grd[k] + off[k][2 * lh], grd[k] + off[k][2 * lh + 1], rows,
+                                                 net[k]->dims[lh], net[k]->dims[lh + 1], sq[k] + sq_used[k]);
+            }
             sq_used[k] += grp.add_backward_w(ns[k]->dz[l + 1], first ? x0[k] : ns[k]->act[l], net[k]->dims[l],
                                              first ? b->perm : nullptr, grd[k] + off[k][2 * l],
                                              grd[k] + off[k][2 * l + 1], rows, net[k]->dims[l], net[k]->dims[l + 1],

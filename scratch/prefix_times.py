@@ -21,16 +21,19 @@ ppo_batch_train(hp.state, loader, "pol")
 eng = pol._engine
 bufs = eng._bufs(ds, w["B"])
 lib = load()
-names = ["fwd0", "fwd1", "fwd2", "fwd3", "loss", "bwd3", "bwd2", "bwd1", "bwd0", "adam"]
+fused = os.environ.get("PPOAF_NO_HEAD_FUSION") is None
+names = (["fwd0", "fwd1", "fwd2", "loss+heads", "bwd2+dW3", "bwd1", "bwd0", "adam"] if fused else
+         ["fwd0", "fwd1", "fwd2", "fwd3", "loss", "bwd3", "bwd2", "bwd1", "bwd0", "adam"])
+NK = len(names)
 def graph_time(n, reps=20, inner=64):
-    os.environ["PPOAF_STOP_AFTER"] = str(min(n, 9))
+    os.environ["PPOAF_STOP_AFTER"] = str(min(n, NK - 1))
     eng.mb_cursor.zero_()
     s = torch.cuda.Stream()
     g = torch.cuda.CUDAGraph()
     with torch.cuda.stream(s):
         def body():
             check(lib.ppoaf_ppo_minibatch_grads(C.byref(eng.cfg), C.byref(bufs), stream_ptr()))
-            if n >= 10: check(lib.ppoaf_ppo_minibatch_apply(C.byref(eng.cfg), C.byref(bufs), stream_ptr()))
+            if n >= NK: check(lib.ppoaf_ppo_minibatch_apply(C.byref(eng.cfg), C.byref(bufs), stream_ptr()))
         body(); torch.cuda.synchronize()
         with torch.cuda.graph(g, stream=s):
             for _ in range(inner): body()
@@ -42,7 +45,7 @@ def graph_time(n, reps=20, inner=64):
             best = min(best, e0.elapsed_time(e1) * 1e3 / inner)
     return best
 prev = 0.0
-for n in range(1, 11):
+for n in range(1, NK + 1):
     t = graph_time(n)
-    print(f"{names[n-1]:6s} cumulative {t:7.2f} us   delta {t - prev:6.2f} us", flush=True)
+    print(f"{names[n-1]:10s} cumulative {t:7.2f} us   delta {t - prev:6.2f} us", flush=True)
     prev = t
