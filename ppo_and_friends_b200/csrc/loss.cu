@@ -24,6 +24,8 @@ constexpr int kPartialStride = kLossScalars + kMaxAct;
 constexpr int kFusedMaxPred = 24;           // actor head outputs
 constexpr int kFusedMaxChunks = 2;          // hidden width <= 256: lane gl owns columns 4 (gl + 32 c) .. + 3
 constexpr int kFusedPredLd = kFusedMaxPred + 1;
+constexpr int kPB = 8;                      // head rows are processed in blocks of 8 independent rows
+constexpr int kFusedStageSlots = kFusedMaxPred * (kG * kFusedMaxChunks) / 256;   // float4 per thread to stage W_actor
 
 bool loss_head_fusable(int pred_dim, int Ha, int Hc, int vf_clip_enabled) {
     auto ok = [](int H) { return H % 4 == 0 && H >= 4 && H <= 4 * kG * kFusedMaxChunks; };
@@ -59,6 +61,13 @@ __device__ __forceinline__ float group_max(float v) {
     return v;
 }
 
+#ifdef PPOAF_GEMM_TIMING
+__device__ long long g_loss_stamps[16];
+#define LOSS_STAMP(k) do { if (threadIdx.x == 0 && (blockIdx.x == 0 || (k) >= 8)) g_loss_stamps[k] = clock64() - t_entry; } while (0)
+#else
+#define LOSS_STAMP(k) do {} while (0)
+#endif
+
 template <bool FUSED>
 __global__ void __launch_bounds__(kLossThreads) ppo_loss_kernel(const LossArgs a) {
     extern __shared__ __align__(16) float s_dyn[];      // FUSED: W_actor [pred][Ha+4] | W_critic [Hc] | biases | pred | dpred
@@ -67,30 +76,31 @@ __global__ void __launch_bounds__(kLossThreads) ppo_loss_kernel(const LossArgs a
     __shared__ double s_tot[kPartialStride];
     __shared__ bool s_last;
 
+#ifdef PPOAF_GEMM_TIMING
+    const long long t_entry = clock64();
+#endif
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int gl = tid & (kG - 1);                                   // lane inside the sample group
     const int i = blockIdx.x * kSamplesPerBlock + tid / kG;          // sample of this group
     const bool live = i < a.batch;
-    const int cur = *a.cursor;
-    const int64_t* idx = a.perm + int64_t(cur) * a.batch_size;
     const float inv_b = 1.0f / float(a.batch);
     const float w_ent = float(a.hparams[PPOAF_HP_ENTROPY_WEIGHT]);
     const float clip_lo = float(1.0 - a.hparams[PPOAF_HP_SURR_CLIP]), clip_hi = float(1.0 + a.hparams[PPOAF_HP_SURR_CLIP]);
     const float vf_clip = float(a.hparams[PPOAF_HP_VF_CLIP]);
     const bool gaussian = a.head == PPOAF_HEAD_GAUSSIAN_TANH;
-
-    if (gaussian && tid < a.act_dim) {
-        // std = max(softplus(log_std), min_std)  (distributions.py:514-515) and d std / d log_std
-        const float ls = a.log_std[tid];
-        const float sp = softplus_torch(ls);
-        s_sd[tid] = fmaxf(sp, a.min_std);
-        const float sig = ls > 20.f ? 1.f : 1.f / (1.f + expf(-ls));
-        s_dsd[tid] = sp > a.min_std ? sig : (sp == a.min_std ? 0.5f * sig : 0.f);
-    }
-    // ---- all global loads of the sample are issued before the staging barrier (one L2 round trip, not three) ----
-    const int64_t j = live ? idx[i] : 0;
     const int smp = tid / kG;                                        // sample slot inside the CTA
+
+    // ---- every global load that does not depend on the cursor is issued first: the hidden activations of this
+    // sample and the head weights travel while the cursor -> permutation -> dataset chain resolves ----
+    const int prows = (a.pred_dim + kPB - 1) / kPB * kPB;            // head rows padded to whole blocks of kPB
+    const int ldw = a.Ha + 4;                                        // rows of W_actor land on distinct bank groups
+    float* s_wa = s_dyn;                                             // [prows][ldw]
+    float* s_wc = s_wa + prows * ldw;                                // [Hc]
+    float* s_b = s_wc + a.Hc;                                        // [pred + 1]
+    float* s_pred = s_b + ((a.pred_dim + 1 + 3) & ~3);               // [samples per block][kFusedPredLd]
+    float* s_dpred = s_pred + kSamplesPerBlock * kFusedPredLd;
     float4 ha[kFusedMaxChunks], hc[kFusedMaxChunks];
+    float4 wreg[kFusedStageSlots];
     if constexpr (FUSED) {
         const float* hra = a.h_actor + int64_t(live ? i : 0) * a.Ha + 4 * gl;
         const float* hrc = a.h_critic + int64_t(live ? i : 0) * a.Hc + 4 * gl;
@@ -100,42 +110,59 @@ __global__ void __launch_bounds__(kLossThreads) ppo_loss_kernel(const LossArgs a
             ha[c] = (col < a.Ha && live) ? *reinterpret_cast<const float4*>(hra + 4 * kG * c) : make_float4(0.f, 0.f, 0.f, 0.f);
             hc[c] = (col < a.Hc && live) ? *reinterpret_cast<const float4*>(hrc + 4 * kG * c) : make_float4(0.f, 0.f, 0.f, 0.f);
         }
-    }
-    float adv = live ? a.advantages[j] : 0.f;
-    const float lp_old = live ? a.log_probs[j] : 0.f;
-    float target = live ? a.rewards_to_go[j] : 0.f;
-    if (a.pf_rows[0] && live) {
-        // pull the NEXT minibatch's observation rows into L2 while this step's backward pass runs: the first-layer
-        // GEMMs of the next step then gather from L2 instead of HBM
-        const int64_t nxt = int64_t(cur + 1) * a.batch_size + i;
-        if (nxt < a.n_flat) {
-            const int64_t jn = a.perm[nxt];
-            const char* r0 = reinterpret_cast<const char*>(a.pf_rows[0]) + jn * a.pf_row_bytes[0];
-            const char* r1 = reinterpret_cast<const char*>(a.pf_rows[1]) + jn * a.pf_row_bytes[1];
-            for (int o = gl * 128; o < a.pf_row_bytes[0]; o += kG * 128) asm volatile("prefetch.global.L2 [%0];" ::"l"(r0 + o));
-            for (int o = gl * 128; o < a.pf_row_bytes[1]; o += kG * 128) asm volatile("prefetch.global.L2 [%0];" ::"l"(r1 + o));
+        const int qa = a.Ha / 4;
+#pragma unroll
+        for (int k = 0; k < kFusedStageSlots; ++k) {                 // W_actor, coalesced 16-byte loads into registers
+            const int t = tid + k * kLossThreads;
+            const int row = t / qa, c4 = t - row * qa;
+            wreg[k] = row < a.pred_dim ? *reinterpret_cast<const float4*>(a.W_actor + int64_t(row) * a.Ha + 4 * c4)
+                                       : make_float4(0.f, 0.f, 0.f, 0.f);
         }
     }
+    const int cur = *a.cursor;
+    const int64_t* idx = a.perm + int64_t(cur) * a.batch_size;
+    const int64_t j = live ? idx[i] : 0;
+    const int64_t nxt = int64_t(cur + 1) * a.batch_size + i;
+    const int64_t jn = (a.pf_rows[0] && live && nxt < a.n_flat) ? a.perm[nxt] : -1;
+    float adv_mu = 0.f, adv_sd = 1.f, val_mu = 0.f, val_sd = 1.f;    // this minibatch's normalisation constants
+    if (a.normalize_adv) { adv_mu = a.mb_adv_stats[2 * cur]; adv_sd = a.mb_adv_stats[2 * cur + 1]; }
+    if (a.normalize_values) { val_mu = a.mb_val_stats[2 * cur]; val_sd = a.mb_val_stats[2 * cur + 1]; }
 
-    // ---- fused heads: stage the two head layers' weights (coalesced 16-byte loads) ----
-    const int ldw = a.Ha + 4;                                        // rows of W_actor land on distinct bank groups
-    float* s_wa = s_dyn;
-    float* s_wc = s_wa + a.pred_dim * ldw;
-    float* s_b = s_wc + a.Hc;                                        // [pred + 1]
-    float* s_pred = s_b + ((a.pred_dim + 1 + 3) & ~3);               // [samples per block][kFusedPredLd]
-    float* s_dpred = s_pred + kSamplesPerBlock * kFusedPredLd;
+    if (gaussian && tid < a.act_dim) {
+        // std = max(softplus(log_std), min_std)  (distributions.py:514-515) and d std / d log_std
+        const float ls = a.log_std[tid];
+        const float sp = softplus_torch(ls);
+        s_sd[tid] = fmaxf(sp, a.min_std);
+        const float sig = ls > 20.f ? 1.f : 1.f / (1.f + expf(-ls));
+        s_dsd[tid] = sp > a.min_std ? sig : (sp == a.min_std ? 0.5f * sig : 0.f);
+    }
     if constexpr (FUSED) {
         const int qa = a.Ha / 4;
-        for (int t = tid; t < a.pred_dim * qa; t += kLossThreads) {
+#pragma unroll
+        for (int k = 0; k < kFusedStageSlots; ++k) {
+            const int t = tid + k * kLossThreads;
             const int row = t / qa, c4 = t - row * qa;
-            *reinterpret_cast<float4*>(s_wa + row * ldw + 4 * c4) = *reinterpret_cast<const float4*>(a.W_actor + int64_t(row) * a.Ha + 4 * c4);
+            if (row < prows) *reinterpret_cast<float4*>(s_wa + row * ldw + 4 * c4) = wreg[k];   // padding rows are zero
         }
         for (int t = tid; t < a.Hc / 4; t += kLossThreads)
             *reinterpret_cast<float4*>(s_wc + 4 * t) = *reinterpret_cast<const float4*>(a.W_critic + 4 * t);
         if (tid < a.pred_dim) s_b[tid] = a.b_actor[tid];
         if (tid == 0) s_b[a.pred_dim] = a.b_critic[0];
     }
+    float adv = live ? a.advantages[j] : 0.f;
+    const float lp_old = live ? a.log_probs[j] : 0.f;
+    float target = live ? a.rewards_to_go[j] : 0.f;
+    if (jn >= 0) {
+        // pull the NEXT minibatch's observation rows into L2 while this step's backward pass runs: the first-layer
+        // GEMMs of the next step then gather from L2 instead of HBM
+        const char* r0 = reinterpret_cast<const char*>(a.pf_rows[0]) + jn * a.pf_row_bytes[0];
+        const char* r1 = reinterpret_cast<const char*>(a.pf_rows[1]) + jn * a.pf_row_bytes[1];
+        for (int o = gl * 128; o < a.pf_row_bytes[0]; o += kG * 128) asm volatile("prefetch.global.L2 [%0];" ::"l"(r0 + o));
+        for (int o = gl * 128; o < a.pf_row_bytes[1]; o += kG * 128) asm volatile("prefetch.global.L2 [%0];" ::"l"(r1 + o));
+    }
+    LOSS_STAMP(0);
     __syncthreads();
+    LOSS_STAMP(1);
 
     float sc[kLossScalars];
 #pragma unroll
@@ -144,8 +171,8 @@ __global__ void __launch_bounds__(kLossThreads) ppo_loss_kernel(const LossArgs a
 #pragma unroll
     for (int k = 0; k < kPerLane; ++k) dsd[k] = 0.f;
 
-    if (a.normalize_adv) adv = (adv - a.mb_adv_stats[2 * cur]) / a.mb_adv_stats[2 * cur + 1];
-    if (a.normalize_values) target = (target - a.mb_val_stats[2 * cur]) / a.mb_val_stats[2 * cur + 1];
+    if (a.normalize_adv) adv = (adv - adv_mu) / adv_sd;
+    if (a.normalize_values) target = (target - val_mu) / val_sd;
     // ---- fused heads, forward: every lane dots its columns of the hidden activations with all head rows, the 8
     // lanes of the sample fold their partial sums, and the outputs go to shared memory ----
     float v_fused = 0.f;
@@ -157,12 +184,16 @@ __global__ void __launch_bounds__(kLossThreads) ppo_loss_kernel(const LossArgs a
         for (int c = 0; c < kFusedMaxChunks; ++c) {
             const int col = 4 * (gl + kG * c);
             if (col < a.Ha) {
-                const float* wcol = s_wa + col;
 #pragma unroll
-                for (int d = 0; d < kFusedMaxPred; ++d) {
-                    if (d < a.pred_dim) {
-                        const float4 w = *reinterpret_cast<const float4*>(wcol + d * ldw);
-                        acc[d] = fmaf(ha[c].x, w.x, fmaf(ha[c].y, w.y, fmaf(ha[c].z, w.z, fmaf(ha[c].w, w.w, acc[d]))));
+                for (int db = 0; db < kFusedMaxPred / kPB; ++db) {
+                    if (db * kPB < a.pred_dim) {                     // uniform: whole blocks of independent rows
+                        float4 w[kPB];
+#pragma unroll
+                        for (int e = 0; e < kPB; ++e) w[e] = *reinterpret_cast<const float4*>(s_wa + (db * kPB + e) * ldw + col);
+#pragma unroll
+                        for (int e = 0; e < kPB; ++e)
+                            acc[db * kPB + e] = fmaf(ha[c].x, w[e].x, fmaf(ha[c].y, w[e].y, fmaf(ha[c].z, w[e].z,
+                                                fmaf(ha[c].w, w[e].w, acc[db * kPB + e]))));
                     }
                 }
             }
@@ -171,16 +202,28 @@ __global__ void __launch_bounds__(kLossThreads) ppo_loss_kernel(const LossArgs a
                 v_fused = fmaf(hc[c].x, w.x, fmaf(hc[c].y, w.y, fmaf(hc[c].z, w.z, fmaf(hc[c].w, w.w, v_fused))));
             }
         }
-        v_fused = group_sum(v_fused) + s_b[a.pred_dim];
+        LOSS_STAMP(2);
+        // fold over the 32 lanes by recursive halving: at every step a lane keeps half of its values and trades the
+        // other half with its partner, so 32 value slots cost 16+8+4+2+1 shuffles and lane l ends with the total of
+        // slot l (slots 0..23: actor outputs, slot 24: the critic output)
+        float v32[32];
 #pragma unroll
-        for (int d = 0; d < kFusedMaxPred; ++d) {
-            if (d < a.pred_dim) {
-                const float t = group_sum(acc[d]);
-                if ((d & (kG - 1)) == gl) s_pred[smp * kFusedPredLd + d] = t + s_b[d];
+        for (int d = 0; d < 32; ++d) v32[d] = d < kFusedMaxPred ? acc[d] : (d == kFusedMaxPred ? v_fused : 0.f);
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            const bool up = (lane & o) != 0;
+#pragma unroll
+            for (int k = 0; k < o; ++k) {
+                const float send = up ? v32[k] : v32[k + o];
+                const float keep = up ? v32[k + o] : v32[k];
+                v32[k] = keep + __shfl_xor_sync(kFull, send, o);
             }
         }
+        v_fused = __shfl_sync(kFull, v32[0], kFusedMaxPred) + s_b[a.pred_dim];
+        if (gl < a.pred_dim) s_pred[smp * kFusedPredLd + gl] = v32[0] + s_b[gl];
         __syncwarp();                                                // the lanes of a sample share one warp
     }
+    LOSS_STAMP(3);
     const float v = FUSED ? (live ? v_fused : 0.f) : (live ? a.critic_out[i] : 0.f);
     if (live && gl == 0) a.values[j] = v;                            // dataset.values[batch_idxs] = values (ppo.py:2340)
     float bad_value = isnan(v) ? 1.f : 0.f;
@@ -323,6 +366,7 @@ __global__ void __launch_bounds__(kLossThreads) ppo_loss_kernel(const LossArgs a
         }
     }
 
+    LOSS_STAMP(4);
     // ---------------- critic ----------------
     float dv1 = 0.f;
     if (FUSED || (gl == 0 && live)) sc[LS_CRITIC] = critic_term(v, target, a.use_huber, dv1);
@@ -355,14 +399,18 @@ __global__ void __launch_bounds__(kLossThreads) ppo_loss_kernel(const LossArgs a
         for (int c = 0; c < kFusedMaxChunks; ++c) {
             const int col = 4 * (gl + kG * c);
             if (col < a.Ha) {
-                const float* wcol = s_wa + col;
                 float t[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
-                for (int d = 0; d < kFusedMaxPred; ++d) {
-                    if (d < a.pred_dim) {
-                        const float4 w = *reinterpret_cast<const float4*>(wcol + d * ldw);
-                        t[0] = fmaf(dp[d], w.x, t[0]); t[1] = fmaf(dp[d], w.y, t[1]);
-                        t[2] = fmaf(dp[d], w.z, t[2]); t[3] = fmaf(dp[d], w.w, t[3]);
+                for (int db = 0; db < kFusedMaxPred / kPB; ++db) {
+                    if (db * kPB < a.pred_dim) {                     // padding rows of s_wa are zero
+                        float4 w[kPB];
+#pragma unroll
+                        for (int e = 0; e < kPB; ++e) w[e] = *reinterpret_cast<const float4*>(s_wa + (db * kPB + e) * ldw + col);
+#pragma unroll
+                        for (int e = 0; e < kPB; ++e) {
+                            t[0] = fmaf(dp[db * kPB + e], w[e].x, t[0]); t[1] = fmaf(dp[db * kPB + e], w[e].y, t[1]);
+                            t[2] = fmaf(dp[db * kPB + e], w[e].z, t[2]); t[3] = fmaf(dp[db * kPB + e], w[e].w, t[3]);
+                        }
                     }
                 }
                 const float y[4] = {ha[c].x, ha[c].y, ha[c].z, ha[c].w};
@@ -379,21 +427,18 @@ __global__ void __launch_bounds__(kLossThreads) ppo_loss_kernel(const LossArgs a
         }
     }
 
+    LOSS_STAMP(5);
     // ---------------- CTA reduction (fp64, fixed order) ----------------
+    // one warp per sample: lane 0 holds the sample's scalars, lane l holds d(loss)/d(std) of dims l, l + 32
+    static_assert(kG == 32, "the reduction below assumes one warp per sample");
     const int n_extra = gaussian ? a.act_dim : 0;
+    if (lane == 0) {
 #pragma unroll
-    for (int k = 0; k < kLossScalars; ++k) {
-        const double w = warp_sum(double(sc[k]));
-        if (lane == 0) s_red[warp][k] = w;
+        for (int k = 0; k < kLossScalars; ++k) s_red[warp][k] = double(sc[k]);
     }
     if (gaussian) {
 #pragma unroll
-        for (int k = 0; k < kPerLane; ++k) {
-            double w = double(dsd[k]);                   // sum over the sample-groups that share the warp
-#pragma unroll
-            for (int o = kG; o < 32; o <<= 1) w += __shfl_xor_sync(kFull, w, o);
-            if (lane < kG) s_red[warp][kLossScalars + lane + k * kG] = w;
-        }
+        for (int k = 0; k < kPerLane; ++k) s_red[warp][kLossScalars + lane + k * kG] = double(dsd[k]);
     }
     __syncthreads();
     const int n_vals = kLossScalars + n_extra;
@@ -404,18 +449,44 @@ __global__ void __launch_bounds__(kLossThreads) ppo_loss_kernel(const LossArgs a
         for (int w = 0; w < kLossThreads / 32; ++w) t += s_red[w][tid];
         part[size_t(blockIdx.x) * kPartialStride + tid] = t;
     }
+    LOSS_STAMP(6);
     __threadfence();
     __syncthreads();
     if (tid == 0) s_last = atomicAdd(a.ticket, 1u) == gridDim.x - 1;
     __syncthreads();
+    LOSS_STAMP(7);
     if (!s_last) return;
     __threadfence();
+    LOSS_STAMP(8);
 
     // ---------------- last CTA: totals -> d(log_std), epoch statistics, value-clip weights -----------
+    // thread (slot = tid % 32, subset = tid / 32) sums CTAs subset, subset + 8, ... for values slot, slot + 32, slot + 64
+    // (all loads independent and in flight at once); the 8 subsets are then added in a fixed order
+    {
+        constexpr int kSub = kLossThreads / 32, kSlots = (kPartialStride + 31) / 32;
+        double acc3[kSlots];
+#pragma unroll
+        for (int q = 0; q < kSlots; ++q) acc3[q] = 0.0;
+        for (unsigned b = warp; b < gridDim.x; b += kSub) {
+#pragma unroll
+            for (int q = 0; q < kSlots; ++q) {
+                const int vi = lane + 32 * q;
+                if (vi < n_vals) acc3[q] += __ldcg(&part[size_t(b) * kPartialStride + vi]);
+            }
+        }
+#pragma unroll
+        for (int q = 0; q < kSlots; ++q) {
+            const int vi = lane + 32 * q;
+            if (vi < kPartialStride) s_red[warp][vi] = acc3[q];
+        }
+    }
+    __syncthreads();
+    __shared__ double s_sq[kLossThreads / 32];
     double my_sq = 0.0;
     if (tid < n_vals) {
         double t = 0.0;
-        for (unsigned b = 0; b < gridDim.x; ++b) t += __ldcg(&part[size_t(b) * kPartialStride + tid]);
+#pragma unroll
+        for (int w = 0; w < kLossThreads / 32; ++w) t += s_red[w][tid];
         s_tot[tid] = t;
         if (tid >= kLossScalars) {
             const float gls = float(t) * s_dsd[tid - kLossScalars];
@@ -423,16 +494,15 @@ __global__ void __launch_bounds__(kLossThreads) ppo_loss_kernel(const LossArgs a
             my_sq = double(gls) * double(gls);
         }
     }
-    if (a.sq_log_std) {                                    // sum of squares of d(log_std) for the gradient-norm clip
-        __shared__ double s_sq[kLossThreads / 32];
-        const double w = warp_sum(my_sq);
-        if (lane == 0) s_sq[warp] = w;
-        __syncthreads();
-        if (tid == 0) {
-            double t = 0.0;
-            for (int k = 0; k < kLossThreads / 32; ++k) t += s_sq[k];
-            *a.sq_log_std = t;
-        }
+    my_sq = warp_sum(my_sq);
+    LOSS_STAMP(9);
+    if (lane == 0) s_sq[warp] = my_sq;
+    __syncthreads();
+    if (tid == 0 && a.sq_log_std) {                        // sum of squares of d(log_std) for the gradient-norm clip
+        double t = 0.0;
+#pragma unroll
+        for (int k = 0; k < kLossThreads / 32; ++k) t += s_sq[k];
+        *a.sq_log_std = t;
     }
     __syncthreads();
     if (tid == 0) {
@@ -449,15 +519,20 @@ __global__ void __launch_bounds__(kLossThreads) ppo_loss_kernel(const LossArgs a
             float* wsel = reinterpret_cast<float*>(part + size_t(gridDim.x) * kPartialStride);
             wsel[0] = w1; wsel[1] = w2;
         }
-        a.epoch_stats[PPOAF_ST_ACTOR_LOSS] += double(actor_mean);
-        a.epoch_stats[PPOAF_ST_CRITIC_LOSS] += double(critic_mean);
-        if (w_ent != 0.f) a.epoch_stats[PPOAF_ST_ENTROPY] += double(float(s_tot[LS_ENTROPY] / nb));
-        a.epoch_stats[PPOAF_ST_KL] += double(float(s_tot[LS_KL] / nb));
-        a.epoch_stats[PPOAF_ST_COUNTER] += 1.0;
-        a.epoch_stats[PPOAF_ST_BAD_RATIO] += s_tot[LS_BAD_RATIO];
-        a.epoch_stats[PPOAF_ST_BAD_VALUE] += s_tot[LS_BAD_VALUE];
+        const double e0 = a.epoch_stats[PPOAF_ST_ACTOR_LOSS], e1 = a.epoch_stats[PPOAF_ST_CRITIC_LOSS];
+        const double e2 = a.epoch_stats[PPOAF_ST_ENTROPY], e3 = a.epoch_stats[PPOAF_ST_KL];
+        const double e4 = a.epoch_stats[PPOAF_ST_COUNTER], e5 = a.epoch_stats[PPOAF_ST_BAD_RATIO];
+        const double e6 = a.epoch_stats[PPOAF_ST_BAD_VALUE];            // seven independent loads, then the stores
+        a.epoch_stats[PPOAF_ST_ACTOR_LOSS] = e0 + double(actor_mean);
+        a.epoch_stats[PPOAF_ST_CRITIC_LOSS] = e1 + double(critic_mean);
+        if (w_ent != 0.f) a.epoch_stats[PPOAF_ST_ENTROPY] = e2 + double(float(s_tot[LS_ENTROPY] / nb));
+        a.epoch_stats[PPOAF_ST_KL] = e3 + double(float(s_tot[LS_KL] / nb));
+        a.epoch_stats[PPOAF_ST_COUNTER] = e4 + 1.0;
+        a.epoch_stats[PPOAF_ST_BAD_RATIO] = e5 + s_tot[LS_BAD_RATIO];
+        a.epoch_stats[PPOAF_ST_BAD_VALUE] = e6 + s_tot[LS_BAD_VALUE];
         *a.ticket = 0u;  // ready for the next launch
     }
+    LOSS_STAMP(10);
 }
 
 __global__ void vf_select_kernel(float* __restrict__ d_critic_out, int batch, const float* __restrict__ wsel) {
@@ -478,7 +553,7 @@ int launch_ppo_loss(const LossArgs& a, cudaStream_t s) {
     const int blocks = (a.batch + kSamplesPerBlock - 1) / kSamplesPerBlock;
     if (a.fused) {
         PPOAF_CHECK_ARG(loss_head_fusable(a.pred_dim, a.Ha, a.Hc, a.vf_clip_enabled), "ppo loss: head layers are not fusable");
-        const size_t smem = sizeof(float) * size_t(a.pred_dim * (a.Ha + 4) + a.Hc + ((a.pred_dim + 1 + 3) & ~3) +
+        const size_t smem = sizeof(float) * size_t((a.pred_dim + kPB - 1) / kPB * kPB * (a.Ha + 4) + a.Hc + ((a.pred_dim + 1 + 3) & ~3) +
                                                    2 * kSamplesPerBlock * kFusedPredLd);
         ppo_loss_kernel<true><<<blocks, kLossThreads, smem, s>>>(a);
     } else {
@@ -495,6 +570,12 @@ int launch_ppo_loss(const LossArgs& a, cudaStream_t s) {
 }
 
 }  // namespace ppoaf
+
+#ifdef PPOAF_GEMM_TIMING
+extern "C" int ppoaf_debug_loss_stamps(long long* out_host) {
+    return cudaMemcpyFromSymbol(out_host, ppoaf::g_loss_stamps, sizeof(long long) * 16) == cudaSuccess ? 0 : 1;
+}
+#endif
 
 // ---- stand-alone head evaluation (PPOPolicy.evaluate's distribution half, policies/ppo_policy.py:939-950) ----
 namespace ppoaf {

@@ -12,6 +12,8 @@
 namespace ppoaf {
 
 constexpr int kOptThreads = 256;
+constexpr int kAdamThreads = 1024;      // adam_update_kernel: 148 x 1024 threads, two float4 slots each, cover 1.2 M parameters in one pass
+constexpr int kAdamSlots = 2;
 
 // Norm pass for the multi-rank path: fixed-order fp64 partials per CTA, no atomics.
 __global__ void __launch_bounds__(kOptThreads)
@@ -31,7 +33,25 @@ grad_sumsq_kernel(const float* __restrict__ grads, int64_t n_actor, int64_t n_to
     if (threadIdx.x == 0) { part_a[blockIdx.x] = sa; part_c[blockIdx.x] = sc; }
 }
 
-__global__ void __launch_bounds__(kOptThreads)
+struct AdamScalars { float neg_step_size, bc2_sqrt, w1, beta2, w2, eps, inv_world; };
+__device__ __forceinline__ void adam_vec(float4& pq, const float4& gq, float4& mq, float4& vq, float coef, const AdamScalars& c) {
+    float g[4] = {gq.x, gq.y, gq.z, gq.w}, p[4] = {pq.x, pq.y, pq.z, pq.w};
+    float mm[4] = {mq.x, mq.y, mq.z, mq.w}, vv[4] = {vq.x, vq.y, vq.z, vq.w};
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        // explicit _rn intrinsics: same operation order as torch's CPU kernels, no FMA contraction
+        const float gk = __fmul_rn(__fmul_rn(g[k], c.inv_world), coef);
+        mm[k] = __fadd_rn(mm[k], __fmul_rn(c.w1, __fsub_rn(gk, mm[k])));                   // lerp_(g, 1-b1)
+        vv[k] = __fadd_rn(__fmul_rn(vv[k], c.beta2), __fmul_rn(__fmul_rn(c.w2, gk), gk));   // mul_ ; addcmul_
+        const float denom = __fadd_rn(__fdiv_rn(__fsqrt_rn(vv[k]), c.bc2_sqrt), c.eps);
+        p[k] = __fadd_rn(p[k], __fdiv_rn(__fmul_rn(c.neg_step_size, mm[k]), denom));        // addcdiv_
+    }
+    pq = make_float4(p[0], p[1], p[2], p[3]);
+    mq = make_float4(mm[0], mm[1], mm[2], mm[3]);
+    vq = make_float4(vv[0], vv[1], vv[2], vv[3]);
+}
+
+__global__ void __launch_bounds__(kAdamThreads)
 adam_update_kernel(float* __restrict__ params, const float* __restrict__ grads, float* __restrict__ m,
                    float* __restrict__ v, int64_t n_actor, int64_t n_total, const double* __restrict__ sq_a,
                    int n_sq_a, const double* __restrict__ sq_c, int n_sq_c, const double* __restrict__ hp,
@@ -40,6 +60,22 @@ adam_update_kernel(float* __restrict__ params, const float* __restrict__ grads, 
     __shared__ double s_pw[2];
     __shared__ float s_coef[2];
     double* pw = reinterpret_cast<double*>(ticket + 2);   // cached (t, beta1^t, beta2^t)
+    const int64_t nv = n_total / 4, na = n_actor / 4;
+    const int64_t stride = int64_t(gridDim.x) * blockDim.x;
+    const int64_t i0 = int64_t(blockIdx.x) * blockDim.x + threadIdx.x;
+    float4* p4 = reinterpret_cast<float4*>(params);
+    const float4* g4 = reinterpret_cast<const float4*>(grads);
+    float4* m4 = reinterpret_cast<float4*>(m);
+    float4* v4 = reinterpret_cast<float4*>(v);
+
+    // ---- the first kAdamSlots float4 slots of every thread are in flight while the scalars are derived ----
+    float4 G[kAdamSlots], P[kAdamSlots], M[kAdamSlots], V[kAdamSlots];
+#pragma unroll
+    for (int k = 0; k < kAdamSlots; ++k) {
+        const int64_t i = i0 + k * stride;
+        if (i < nv) { G[k] = g4[i]; P[k] = p4[i]; M[k] = m4[i]; V[k] = v4[i]; }
+    }
+
     // ---- fold the sum-of-squares slots (same order in every CTA -> identical scalars everywhere) ----
     double ta = 0.0, tc = 0.0;
     for (int k = threadIdx.x; k < n_sq_a; k += blockDim.x) ta += sq_a[k];
@@ -75,32 +111,22 @@ adam_update_kernel(float* __restrict__ params, const float* __restrict__ grads, 
         s_f[5] = float(hp[PPOAF_HP_ADAM_EPS]);
     }
     __syncthreads();
-    const float neg_step_size = s_f[0], bc2_sqrt = s_f[1], w1 = s_f[2], beta2 = s_f[3], w2 = s_f[4], eps = s_f[5];
+    const AdamScalars c{s_f[0], s_f[1], s_f[2], s_f[3], s_f[4], s_f[5], inv_world};
     const float coef_a = s_coef[0], coef_c = s_coef[1];
 
-    const int64_t nv = n_total / 4, na = n_actor / 4;
-    float4* p4 = reinterpret_cast<float4*>(params);
-    const float4* g4 = reinterpret_cast<const float4*>(grads);
-    float4* m4 = reinterpret_cast<float4*>(m);
-    float4* v4 = reinterpret_cast<float4*>(v);
-    for (int64_t i = int64_t(blockIdx.x) * blockDim.x + threadIdx.x; i < nv; i += int64_t(gridDim.x) * blockDim.x) {
-        const float coef = i < na ? coef_a : coef_c;
+#pragma unroll
+    for (int k = 0; k < kAdamSlots; ++k) {
+        const int64_t i = i0 + k * stride;
+        if (i < nv) {
+            adam_vec(P[k], G[k], M[k], V[k], i < na ? coef_a : coef_c, c);
+            p4[i] = P[k]; m4[i] = M[k]; v4[i] = V[k];
+        }
+    }
+    for (int64_t i = i0 + kAdamSlots * stride; i < nv; i += stride) {      // networks beyond 1.2 M parameters
         const float4 gq = g4[i];
         float4 pq = p4[i], mq = m4[i], vq = v4[i];
-        float g[4] = {gq.x, gq.y, gq.z, gq.w}, p[4] = {pq.x, pq.y, pq.z, pq.w};
-        float mm[4] = {mq.x, mq.y, mq.z, mq.w}, vv[4] = {vq.x, vq.y, vq.z, vq.w};
-#pragma unroll
-        for (int k = 0; k < 4; ++k) {
-            // explicit _rn intrinsics: same operation order as torch's CPU kernels, no FMA contraction
-            const float gk = __fmul_rn(__fmul_rn(g[k], inv_world), coef);
-            mm[k] = __fadd_rn(mm[k], __fmul_rn(w1, __fsub_rn(gk, mm[k])));                 // lerp_(g, 1-b1)
-            vv[k] = __fadd_rn(__fmul_rn(vv[k], beta2), __fmul_rn(__fmul_rn(w2, gk), gk));   // mul_ ; addcmul_
-            const float denom = __fadd_rn(__fdiv_rn(__fsqrt_rn(vv[k]), bc2_sqrt), eps);
-            p[k] = __fadd_rn(p[k], __fdiv_rn(__fmul_rn(neg_step_size, mm[k]), denom));      // addcdiv_
-        }
-        p4[i] = make_float4(p[0], p[1], p[2], p[3]);
-        m4[i] = make_float4(mm[0], mm[1], mm[2], mm[3]);
-        v4[i] = make_float4(vv[0], vv[1], vv[2], vv[3]);
+        adam_vec(pq, gq, mq, vq, i < na ? coef_a : coef_c, c);
+        p4[i] = pq; m4[i] = mq; v4[i] = vq;
     }
     // ---- the last CTA to finish advances the counters (every CTA has read adam_step by then) ----
     __syncthreads();
@@ -145,7 +171,9 @@ int launch_clip_adam(float* params, const float* grads, float* m, float* v, int6
         sq_a = partials; sq_c = partials + grid;
         n_sq_a = n_sq_c = grid;
     }
-    adam_update_kernel<<<grid, kOptThreads, 0, s>>>(params, grads, m, v, n_actor, n_total, sq_a, n_sq_a, sq_c, n_sq_c,
+    int64_t agrid = ceil_div64(n_total / 4, kAdamThreads);
+    agrid = agrid < 1 ? 1 : (agrid > sm_count() ? sm_count() : agrid);
+    adam_update_kernel<<<int(agrid), kAdamThreads, 0, s>>>(params, grads, m, v, n_actor, n_total, sq_a, n_sq_a, sq_c, n_sq_c,
                                                     hparams, adam_step, mb_cursor, ticket);
     PPOAF_CHECK_LAUNCH("adam_update_kernel");
     return 0;

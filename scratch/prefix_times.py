@@ -49,3 +49,10 @@ for n in range(1, NK + 1):
     t = graph_time(n)
     print(f"{names[n-1]:10s} cumulative {t:7.2f} us   delta {t - prev:6.2f} us", flush=True)
     prev = t
+if hasattr(lib, "ppoaf_debug_loss_stamps") or True:
+    try:
+        lib.ppoaf_debug_loss_stamps.argtypes = [C.c_void_p]; lib.ppoaf_debug_loss_stamps.restype = C.c_int
+        buf = (C.c_longlong * 16)(); lib.ppoaf_debug_loss_stamps(buf)
+        print("loss kernel stamps (cycles from CTA entry; 0-7 CTA 0, 8-10 last CTA):", list(buf)[:11])
+    except Exception as e:
+        print("no loss stamps", e)
