@@ -4,6 +4,7 @@
 #include <stdint.h>
 #include <stdio.h>
 #include <string.h>
+#include <utility>
 
 #include "../../include/ppoaf_b200.h"
 
@@ -139,6 +140,32 @@ __device__ __forceinline__ void act_bwd4(float (&o)[4], const float (&y)[4], int
 #pragma unroll
         for (int j = 0; j < 4; ++j) o[j] = y[j] > 0.f ? o[j] : 0.01f * o[j];
     }
+}
+
+
+// ---- programmatic dependent launch (PDL) ---------------------------------------------------------------------
+// The minibatch step is a chain of dependent launches.  Launched with the programmatic-serialization attribute, a
+// kernel's CTAs may become resident while the previous kernel is still draining: they run their set-up (barrier
+// initialisation, problem lookup, index arithmetic) and block in pdl_wait() until the previous kernel has completed
+// and its writes are visible.  NOTHING that another kernel of the chain produces may be read, and nothing it reads
+// may be written, before pdl_wait().  pdl_trigger() lets the next kernel's CTAs start arriving; it is always
+// issued AFTER pdl_wait(), so whatever a kernel reads early can only race with its immediate predecessor (every
+// older kernel has completed), which is what the "static operand" flags of the callers are defined against.
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+
+bool pdl_enabled();    // step.cu: PPOAF_PDL=0 turns the attribute off (plain stream order)
+
+template <typename... KArgs, typename... Args>
+inline cudaError_t launch_chain(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t s, Args&&... args) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = s;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = pdl_enabled() ? 1 : 0;
+    return cudaLaunchKernelEx(&cfg, kernel, std::forward<Args>(args)...);
 }
 
 }  // namespace ppoaf

@@ -17,14 +17,16 @@ struct GemmGroup {
     GemmGroup(const GemmGroup&) = delete;
     GemmGroup& operator=(const GemmGroup&) = delete;
     // Y[rows, out] = act(X[idx][rows, in] W^T + b)
+    // w_static / x_static: the operand is not written by the launch that precedes this one in the stream, so the
+    // FFMA kernel may stage it before its programmatic-dependency wait (see common.cuh, PDL)
     void add_forward(const float* X, int ldx, const int64_t* idx, const float* W, const float* b, float* Y, int rows,
-                     int in, int out, int act);
+                     int in, int out, int act, bool w_static = false);
     // dX[rows, in] = (dZ[rows, out] W[out, in]) * act'(Xact[rows, in])
     void add_backward_x(const float* dZ, const float* W, const float* Xact, float* dX, int rows, int in, int out, int act);
     // dW[out, in] = dZ[rows, out]^T X[idx][rows, in]; db[out] = column sums of dZ; sq_out[tile] = tile sum of squares
     // returns the number of sum-of-squares slots (tiles) this problem writes
     int add_backward_w(const float* dZ, const float* X, int ldx, const int64_t* idx, float* dW, float* db, int rows,
-                       int in, int out, double* sq_out);
+                       int in, int out, double* sq_out, bool x_static = false);
     int launch(const int32_t* cursor, int cursor_stride, cudaStream_t s);
 };
 int backward_w_tiles(int in, int out, int backend);
@@ -92,7 +94,7 @@ size_t optim_workspace_bytes();
 // null -> a norm pass over the (all-reduced) gradients is run first.
 int launch_clip_adam(float* params, const float* grads, float* m, float* v, int64_t* adam_step, int32_t* mb_cursor,
                      const double* hparams, int64_t n_actor, int64_t n_critic, const double* sq_a, int n_sq_a,
-                     const double* sq_c, int n_sq_c, void* workspace, cudaStream_t s);
+                     const double* sq_c, int n_sq_c, void* workspace, cudaStream_t s, bool chained);
 int launch_advance_cursor(int32_t* mb_cursor, cudaStream_t s);
 
 }  // namespace ppoaf

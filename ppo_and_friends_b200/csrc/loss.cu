@@ -99,17 +99,11 @@ __global__ void __launch_bounds__(kLossThreads) ppo_loss_kernel(const LossArgs a
     float* s_b = s_wc + a.Hc;                                        // [pred + 1]
     float* s_pred = s_b + ((a.pred_dim + 1 + 3) & ~3);               // [samples per block][kFusedPredLd]
     float* s_dpred = s_pred + kSamplesPerBlock * kFusedPredLd;
+    // Everything up to pdl_wait() reads only data that no launch of the current step writes (parameters, the
+    // dataset, the permutation, the cursor): it overlaps the tail of the previous launch.
     float4 ha[kFusedMaxChunks], hc[kFusedMaxChunks];
     float4 wreg[kFusedStageSlots];
     if constexpr (FUSED) {
-        const float* hra = a.h_actor + int64_t(live ? i : 0) * a.Ha + 4 * gl;
-        const float* hrc = a.h_critic + int64_t(live ? i : 0) * a.Hc + 4 * gl;
-#pragma unroll
-        for (int c = 0; c < kFusedMaxChunks; ++c) {
-            const int col = 4 * (gl + kG * c);
-            ha[c] = (col < a.Ha && live) ? *reinterpret_cast<const float4*>(hra + 4 * kG * c) : make_float4(0.f, 0.f, 0.f, 0.f);
-            hc[c] = (col < a.Hc && live) ? *reinterpret_cast<const float4*>(hrc + 4 * kG * c) : make_float4(0.f, 0.f, 0.f, 0.f);
-        }
         const int qa = a.Ha / 4;
 #pragma unroll
         for (int k = 0; k < kFusedStageSlots; ++k) {                 // W_actor, coalesced 16-byte loads into registers
@@ -136,7 +130,20 @@ __global__ void __launch_bounds__(kLossThreads) ppo_loss_kernel(const LossArgs a
         const float sig = ls > 20.f ? 1.f : 1.f / (1.f + expf(-ls));
         s_dsd[tid] = sp > a.min_std ? sig : (sp == a.min_std ? 0.5f * sig : 0.f);
     }
+    float adv = live ? a.advantages[j] : 0.f;
+    const float lp_old = live ? a.log_probs[j] : 0.f;
+    float target = live ? a.rewards_to_go[j] : 0.f;
+    pdl_wait();
+    pdl_trigger();
     if constexpr (FUSED) {
+        const float* hra = a.h_actor + int64_t(live ? i : 0) * a.Ha + 4 * gl;
+        const float* hrc = a.h_critic + int64_t(live ? i : 0) * a.Hc + 4 * gl;
+#pragma unroll
+        for (int c = 0; c < kFusedMaxChunks; ++c) {
+            const int col = 4 * (gl + kG * c);
+            ha[c] = (col < a.Ha && live) ? *reinterpret_cast<const float4*>(hra + 4 * kG * c) : make_float4(0.f, 0.f, 0.f, 0.f);
+            hc[c] = (col < a.Hc && live) ? *reinterpret_cast<const float4*>(hrc + 4 * kG * c) : make_float4(0.f, 0.f, 0.f, 0.f);
+        }
         const int qa = a.Ha / 4;
 #pragma unroll
         for (int k = 0; k < kFusedStageSlots; ++k) {
@@ -149,9 +156,6 @@ __global__ void __launch_bounds__(kLossThreads) ppo_loss_kernel(const LossArgs a
         if (tid < a.pred_dim) s_b[tid] = a.b_actor[tid];
         if (tid == 0) s_b[a.pred_dim] = a.b_critic[0];
     }
-    float adv = live ? a.advantages[j] : 0.f;
-    const float lp_old = live ? a.log_probs[j] : 0.f;
-    float target = live ? a.rewards_to_go[j] : 0.f;
     if (jn >= 0) {
         // pull the NEXT minibatch's observation rows into L2 while this step's backward pass runs: the first-layer
         // GEMMs of the next step then gather from L2 instead of HBM
@@ -555,9 +559,9 @@ int launch_ppo_loss(const LossArgs& a, cudaStream_t s) {
         PPOAF_CHECK_ARG(loss_head_fusable(a.pred_dim, a.Ha, a.Hc, a.vf_clip_enabled), "ppo loss: head layers are not fusable");
         const size_t smem = sizeof(float) * size_t((a.pred_dim + kPB - 1) / kPB * kPB * (a.Ha + 4) + a.Hc + ((a.pred_dim + 1 + 3) & ~3) +
                                                    2 * kSamplesPerBlock * kFusedPredLd);
-        ppo_loss_kernel<true><<<blocks, kLossThreads, smem, s>>>(a);
+        launch_chain(ppo_loss_kernel<true>, dim3(blocks), dim3(kLossThreads), smem, s, a);
     } else {
-        ppo_loss_kernel<false><<<blocks, kLossThreads, 0, s>>>(a);
+        launch_chain(ppo_loss_kernel<false>, dim3(blocks), dim3(kLossThreads), 0, s, a);
     }
     PPOAF_CHECK_LAUNCH("ppo_loss_kernel");
     if (a.vf_clip_enabled) {

@@ -33,8 +33,9 @@ static GemmProblem* next_problem(GemmGroup* grp, int M, int N) {
 }
 
 void GemmGroup::add_forward(const float* X, int ldx, const int64_t* idx, const float* W, const float* b, float* Y,
-                            int rows, int in, int out, int act) {
+                            int rows, int in, int out, int act, bool w_static) {
     GemmProblem* g = next_problem(this, rows, out);
+    g->b_static = w_static ? 1 : 0;
     g->A = X; g->lda = ldx; g->B = W; g->ldb = in; g->C = Y; g->ldc = out;
     g->M = rows; g->N = out; g->K = in;
     g->idxA = idx; g->bias = b; g->act = act;
@@ -47,6 +48,7 @@ void GemmGroup::add_backward_x(const float* dZ, const float* W, const float* Xac
     g->A = dZ; g->lda = out; g->B = W; g->ldb = in; g->C = dX; g->ldc = in;
     g->M = rows; g->N = in; g->K = out;
     g->aux = Xact; g->ldaux = in; g->act = act;
+    g->b_static = 1;                      // W is only written by the optimizer, several launches back
     g->flavour = EPI_BWD_X * 4 + (vec4_ok(dZ, out, out) ? 2 : 0) + (vec4_ok(W, in, in) ? 1 : 0);
 }
 
@@ -55,8 +57,9 @@ int backward_w_tiles(int in, int out, int backend) {
 }
 
 int GemmGroup::add_backward_w(const float* dZ, const float* X, int ldx, const int64_t* idx, float* dW, float* db,
-                              int rows, int in, int out, double* sq_out) {
+                              int rows, int in, int out, double* sq_out, bool x_static) {
     GemmProblem* g = next_problem(this, out, in);
+    g->b_static = (x_static && idx == nullptr) ? 1 : 0;
     g->A = dZ; g->lda = out; g->B = X; g->ldb = ldx; g->C = dW; g->ldc = in;
     g->M = out; g->N = in; g->K = rows;
     g->idxB = idx; g->dbias = db; g->sq_out = sq_out;
@@ -69,10 +72,10 @@ int GemmGroup::launch(const int32_t* cursor, int cursor_stride, cudaStream_t s) 
     args->cursor = cursor;
     args->cursor_stride = cursor_stride;
     if (backend == GEMM_BACKEND_TCGEN05) {
-        umma::umma_grouped_gemm_kernel<<<n_tiles, umma::kUThreads + 32, umma::kUmmaSmemBytes, s>>>(*args);
+        launch_chain(umma::umma_grouped_gemm_kernel, dim3(n_tiles), dim3(umma::kUThreads + 32), umma::kUmmaSmemBytes, s, *args);
         PPOAF_CHECK_LAUNCH("umma_grouped_gemm_kernel");
     } else {
-        grouped_gemm_kernel<<<n_tiles, kThreads, kGemmSmemBytes, s>>>(*args);
+        launch_chain(grouped_gemm_kernel, dim3(n_tiles), dim3(kThreads), kGemmSmemBytes, s, *args);
         PPOAF_CHECK_LAUNCH("grouped_gemm_kernel");
     }
     return 0;
@@ -163,7 +166,7 @@ extern "C" int ppoaf_mlp_forward(const ppoaf_mlp_desc* net, const float* params,
         float* out = last ? y : buf[l & 1];
         GemmGroup grp(gemm_backend());
         grp.add_forward(in, net->dims[l], in_idx, params + off[2 * l], params + off[2 * l + 1], out, n_rows,
-                        net->dims[l], net->dims[l + 1], last ? PPOAF_ACT_IDENTITY : net->activation);
+                        net->dims[l], net->dims[l + 1], last ? PPOAF_ACT_IDENTITY : net->activation, l > 0);
         if (grp.launch(nullptr, 0, s)) return 2;
         in = out;
         in_idx = nullptr;

@@ -63,6 +63,8 @@ struct GemmProblem {
     int flavour;                    // epi * 4 + (VA == 4) * 2 + (VB == 4)
     int tiles_n;                    // number of tiles along N
     int tile_begin;                 // first linear tile id of this problem inside the launch
+    int b_static;                   // B is not written by the launch right before this one (and has no gather): it may
+                                    //   be staged before the programmatic-dependency wait
 };
 struct GroupedGemmArgs {
     int n_problems;
@@ -237,13 +239,30 @@ __device__ __forceinline__ float4 load4_guarded(const float* p, int remaining, b
 }
 
 template <bool A_RC, bool B_RC, int VA, int VB, int EPI>
-__device__ __forceinline__ void gemm_tile(const GemmProblem& g, int tile, int64_t idx_off, float* smem, uint64_t* bars,
-                                          int* s_idx) {
+__device__ __forceinline__ void gemm_tile(const GemmProblem& g, int tile, const int32_t* cursor, int cursor_stride,
+                                          float* smem, uint64_t* bars, int* s_idx) {
     const int tid = threadIdx.x;
     PPOAF_STAMP(1);
     const int grp = tid >> 5, lane = tid & 31;
     const int tx = lane & 7, ty = lane >> 3;                  // 8 column-lanes x 4 row-lanes per warp
     const int m0 = (tile / g.tiles_n) * kBM, n0 = (tile % g.tiles_n) * kBN;
+
+    // ---- before the dependency wait: a B operand that the previous launch does not write (weights in the forward
+    // and backward-x launches, stored activations in backward-w) starts travelling while that launch drains ----
+    RcStager<kBN, VB> rcb;
+    const bool b_early = g.b_static && !g.idxB;
+    if (b_early) {
+        const int Kr = min(g.K, kKRound), Kr4 = (Kr + 3) & ~3;
+        const int ldsA0 = A_RC ? rc_stride(Kr4) : kBM, ldsB0 = B_RC ? rc_stride(Kr4) : kBN;
+        float* panelB0 = smem + (A_RC ? kBM * ldsA0 : Kr4 * kBM);
+        if constexpr (B_RC) { rcb.plan(g.B, g.ldb, nullptr, n0, g.N, tid); rcb.stage(panelB0, ldsB0, 0, g.K, 0, Kr4, tid); }
+        else stage_oc<kBN, VB>(panelB0, g.B, g.ldb, nullptr, n0, g.N, 0, g.K, 0, Kr4, tid);
+    }
+    pdl_wait();                                    // everything below may read what the previous launch wrote
+    pdl_trigger();                                 // after the wait: the next launch's early reads then only ever
+                                                   //   overlap THIS launch, never the one before it
+    // the minibatch cursor is only needed by the gathering layers: no dependent global load on the others
+    const int64_t idx_off = (cursor && (g.idxA || g.idxB)) ? int64_t(*cursor) * cursor_stride : 0;
     const int64_t* idxA = g.idxA ? g.idxA + idx_off : nullptr;
     const int64_t* idxB = g.idxB ? g.idxB + idx_off : nullptr;
 
@@ -261,9 +280,8 @@ __device__ __forceinline__ void gemm_tile(const GemmProblem& g, int tile, int64_
     int* s_idx_a = s_idx;                      // [kKRound]
     int* s_idx_b = s_idx + kKRound;            // [kKRound]
     RcStager<kBM, VA> rca;
-    RcStager<kBN, VB> rcb;
     if constexpr (A_RC) rca.plan(g.A, g.lda, idxA, m0, g.M, tid);
-    if constexpr (B_RC) rcb.plan(g.B, g.ldb, idxB, n0, g.N, tid);
+    if constexpr (B_RC) { if (!b_early) rcb.plan(g.B, g.ldb, idxB, n0, g.N, tid); }
 
     const int n_rounds = (g.K + kKRound - 1) / kKRound;
 #pragma unroll 1
@@ -287,8 +305,10 @@ __device__ __forceinline__ void gemm_tile(const GemmProblem& g, int tile, int64_
             const int k_hi = min(Kr4, (c + 1) * (kGroups / kLoadGroups) * Kw);
             if constexpr (A_RC) rca.stage(panelA, ldsA, k_base, g.K, k_lo, k_hi, tid);
             else stage_oc<kBM, VA>(panelA, g.A, g.lda, idxA ? s_idx_a : nullptr, m0, g.M, k_base, g.K, k_lo, k_hi, tid);
-            if constexpr (B_RC) rcb.stage(panelB, ldsB, k_base, g.K, k_lo, k_hi, tid);
-            else stage_oc<kBN, VB>(panelB, g.B, g.ldb, idxB ? s_idx_b : nullptr, n0, g.N, k_base, g.K, k_lo, k_hi, tid);
+            if (!(b_early && round == 0)) {
+                if constexpr (B_RC) rcb.stage(panelB, ldsB, k_base, g.K, k_lo, k_hi, tid);
+                else stage_oc<kBN, VB>(panelB, g.B, g.ldb, idxB ? s_idx_b : nullptr, n0, g.N, k_base, g.K, k_lo, k_hi, tid);
+            }
             cp_async_arrive(&bars[c]);
         }
         if (round == 0) PPOAF_STAMP(2);
@@ -423,9 +443,7 @@ __global__ void __launch_bounds__(kThreads) grouped_gemm_kernel(const GroupedGem
         if (i < args.n_problems && int(blockIdx.x) >= args.p[i].tile_begin) p = i;
     const GemmProblem& g = args.p[p];
     const int tile = int(blockIdx.x) - g.tile_begin;
-    // the minibatch cursor is only needed by the gathering layers: no dependent global load on the others
-    const int64_t idx_off = (args.cursor && (g.idxA || g.idxB)) ? int64_t(*args.cursor) * args.cursor_stride : 0;
-#define PPOAF_TILE(ARC, BRC, VA, VB, E) gemm_tile<ARC, BRC, VA, VB, E>(g, tile, idx_off, smem, s_bars, s_idx)
+#define PPOAF_TILE(ARC, BRC, VA, VB, E) gemm_tile<ARC, BRC, VA, VB, E>(g, tile, args.cursor, args.cursor_stride, smem, s_bars, s_idx)
 #ifdef PPOAF_GEMM_REPEAT   // debug: run the tile twice, the stamps of the second (warm instruction cache) pass survive
 #pragma unroll 1
     for (int rep = 0; rep < 2; ++rep) {

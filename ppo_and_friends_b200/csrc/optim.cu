@@ -68,12 +68,20 @@ adam_update_kernel(float* __restrict__ params, const float* __restrict__ grads, 
     float4* m4 = reinterpret_cast<float4*>(m);
     float4* v4 = reinterpret_cast<float4*>(v);
 
-    // ---- the first kAdamSlots float4 slots of every thread are in flight while the scalars are derived ----
+    // ---- the first kAdamSlots float4 slots of every thread are in flight while the scalars are derived; the
+    // parameters and moments (only ever written by this kernel) are fetched before the dependency wait ----
     float4 G[kAdamSlots], P[kAdamSlots], M[kAdamSlots], V[kAdamSlots];
 #pragma unroll
     for (int k = 0; k < kAdamSlots; ++k) {
         const int64_t i = i0 + k * stride;
-        if (i < nv) { G[k] = g4[i]; P[k] = p4[i]; M[k] = m4[i]; V[k] = v4[i]; }
+        if (i < nv) { P[k] = p4[i]; M[k] = m4[i]; V[k] = v4[i]; }
+    }
+    pdl_wait();
+    pdl_trigger();
+#pragma unroll
+    for (int k = 0; k < kAdamSlots; ++k) {
+        const int64_t i = i0 + k * stride;
+        if (i < nv) G[k] = g4[i];
     }
 
     // ---- fold the sum-of-squares slots (same order in every CTA -> identical scalars everywhere) ----
@@ -155,7 +163,7 @@ size_t optim_workspace_bytes() {
 
 int launch_clip_adam(float* params, const float* grads, float* m, float* v, int64_t* adam_step, int32_t* mb_cursor,
                      const double* hparams, int64_t n_actor, int64_t n_critic, const double* sq_a, int n_sq_a,
-                     const double* sq_c, int n_sq_c, void* workspace, cudaStream_t s) {
+                     const double* sq_c, int n_sq_c, void* workspace, cudaStream_t s, bool chained) {
     PPOAF_CHECK_ARG(n_actor % 4 == 0 && n_critic % 4 == 0, "clip_adam: segment sizes must be multiples of 4 floats");
     PPOAF_CHECK_ARG((reinterpret_cast<uintptr_t>(params) | reinterpret_cast<uintptr_t>(grads) |
                      reinterpret_cast<uintptr_t>(m) | reinterpret_cast<uintptr_t>(v)) % 16 == 0,
@@ -173,8 +181,14 @@ int launch_clip_adam(float* params, const float* grads, float* m, float* v, int6
     }
     int64_t agrid = ceil_div64(n_total / 4, kAdamThreads);
     agrid = agrid < 1 ? 1 : (agrid > sm_count() ? sm_count() : agrid);
-    adam_update_kernel<<<int(agrid), kAdamThreads, 0, s>>>(params, grads, m, v, n_actor, n_total, sq_a, n_sq_a, sq_c, n_sq_c,
-                                                    hparams, adam_step, mb_cursor, ticket);
+    // chained: the launch before this one is the last backward GEMM of the step, which never writes params / m / v,
+    // so the kernel may fetch them before its dependency wait.  Stand-alone calls keep plain stream order.
+    if (chained)
+        launch_chain(adam_update_kernel, dim3(int(agrid)), dim3(kAdamThreads), 0, s, params, grads, m, v, n_actor, n_total,
+                     sq_a, n_sq_a, sq_c, n_sq_c, hparams, adam_step, mb_cursor, ticket);
+    else
+        adam_update_kernel<<<int(agrid), kAdamThreads, 0, s>>>(params, grads, m, v, n_actor, n_total, sq_a, n_sq_a, sq_c,
+                                                              n_sq_c, hparams, adam_step, mb_cursor, ticket);
     PPOAF_CHECK_LAUNCH("adam_update_kernel");
     return 0;
 }
@@ -195,5 +209,5 @@ extern "C" int ppoaf_clip_adam_step(float* params, const float* grads, float* ad
     PPOAF_CHECK_ARG(workspace_bytes >= optim_workspace_bytes(), "ppoaf_clip_adam_step: workspace too small");
     PPOAF_CHECK_ARG(reinterpret_cast<uintptr_t>(workspace) % 16 == 0, "ppoaf_clip_adam_step: workspace alignment");
     return launch_clip_adam(params, grads, adam_m, adam_v, adam_step, nullptr, hparams, n_actor, n_critic, nullptr, 0,
-                            nullptr, 0, workspace, (cudaStream_t)stream);
+                            nullptr, 0, workspace, (cudaStream_t)stream, /*chained=*/false);
 }

@@ -23,6 +23,12 @@ void set_error(const char* fmt, ...) {
     va_end(ap);
 }
 
+bool pdl_enabled() {
+    static int cached = -1;
+    if (cached < 0) { const char* e = getenv("PPOAF_PDL"); cached = (e && e[0] == '0') ? 0 : 1; }
+    return cached != 0;
+}
+
 int sm_count() {
     static int cached = 0;
     if (cached > 0) return cached;
@@ -199,7 +205,8 @@ extern "C" int ppoaf_ppo_minibatch_grads(const ppoaf_update_cfg* cfg, const ppoa
             const bool first = l == 0, last = l + 1 == L[k];
             grp.add_forward(first ? x0[k] : ns[k]->act[l], net[k]->dims[l], first ? b->perm : nullptr,
                             par[k] + off[k][2 * l], par[k] + off[k][2 * l + 1], ns[k]->act[l + 1], rows,
-                            net[k]->dims[l], net[k]->dims[l + 1], last ? PPOAF_ACT_IDENTITY : net[k]->activation);
+                            net[k]->dims[l], net[k]->dims[l + 1], last ? PPOAF_ACT_IDENTITY : net[k]->activation,
+                            /*w_static=*/l > 0);
         }
         PPOAF_STEP_LIMIT();
         if (grp.launch(b->mb_cursor, b->batch_size, s)) return 2;
@@ -272,12 +279,13 @@ extern "C" int ppoaf_ppo_minibatch_grads(const ppoaf_update_cfg* cfg, const ppoa
                 const int lh = L[k] - 1;
                 sq_used[k] += grp.add_backward_w(ns[k]->dz[lh + 1], ns[k]->act[lh], net[k]->dims[lh], nullptr,
                                                  grd[k] + off[k][2 * lh], grd[k] + off[k][2 * lh + 1], rows,
-                                                 net[k]->dims[lh], net[k]->dims[lh + 1], sq[k] + sq_used[k]);
+                                                 net[k]->dims[lh], net[k]->dims[lh + 1], sq[k] + sq_used[k],
+                                                 /*x_static=*/true);
             }
             sq_used[k] += grp.add_backward_w(ns[k]->dz[l + 1], first ? x0[k] : ns[k]->act[l], net[k]->dims[l],
                                              first ? b->perm : nullptr, grd[k] + off[k][2 * l],
                                              grd[k] + off[k][2 * l + 1], rows, net[k]->dims[l], net[k]->dims[l + 1],
-                                             sq[k] + sq_used[k]);
+                                             sq[k] + sq_used[k], /*x_static=*/!first);
             if (!first)
                 grp.add_backward_x(ns[k]->dz[l + 1], par[k] + off[k][2 * l], ns[k]->act[l], ns[k]->dz[l], rows,
                                    net[k]->dims[l], net[k]->dims[l + 1], net[k]->activation);
@@ -303,5 +311,6 @@ extern "C" int ppoaf_ppo_minibatch_apply(const ppoaf_update_cfg* cfg, const ppoa
     const bool fused_norm = cfg->world_size <= 1;
     return launch_clip_adam(b->params, b->grads, b->adam_m, b->adam_v, b->adam_step, b->mb_cursor, b->hparams, n_actor,
                             n_critic, fused_norm ? sc.sq_actor : nullptr, sc.n_sq_actor,
-                            fused_norm ? sc.sq_critic : nullptr, sc.n_sq_critic, sc.optim_ws, s);
+                            fused_norm ? sc.sq_critic : nullptr, sc.n_sq_critic, sc.optim_ws, s,
+                            /*chained=*/fused_norm);
 }

@@ -372,6 +372,8 @@ __global__ void __launch_bounds__(kUThreads + 32) umma_grouped_gemm_kernel(const
         if (i < args.n_problems && int(blockIdx.x) >= args.p[i].tile_begin) p = i;
     const GemmProblem& g = args.p[p];
     const int tile = int(blockIdx.x) - g.tile_begin;
+    pdl_wait();
+    pdl_trigger();
     const int64_t idx_off = args.cursor ? int64_t(*args.cursor) * args.cursor_stride : 0;
     switch (g.flavour >> 2) {
         case EPI_FWD:   umma_tile<true, true, EPI_FWD>(g, tile, idx_off, smem, s_bars, tmem); break;
