@@ -152,6 +152,7 @@ typedef struct {
  *   offsets[2*l] = W_l, offsets[2*l+1] = b_l, then log_std (actor only); returns total floats. */
 int64_t ppoaf_param_layout(const ppoaf_mlp_desc* net, int32_t log_std_dim, int64_t* offsets /* [2*L+1] */);
 
+#define PPOAF_MAX_MIRROR 7      /* peers a rank can push its gradients to (R <= 8) */
 typedef struct {
     /* dataset in flat order (PPODataset attributes, utils/episode_info.py:823-912) */
     const float*   critic_obs;    /* [N, Dc] */
@@ -175,6 +176,13 @@ typedef struct {
     int64_t n_flat;               /* N */
     int32_t batch;                /* rows in THIS minibatch (== batch_size except the last one) */
     int32_t batch_size;           /* nominal B: minibatch k covers perm[k*B .. k*B+batch) */
+    /* R > 1, push exchange: every gradient element written to `grads` is also stored at
+     * (char*)address + mirror_delta[q] for q < n_mirror — the slot this rank owns inside every peer's receive
+     * buffer (peer memory mapped with ppoaf_peer_import), so the gradients cross NVLink while the backward pass
+     * is still running.  n_mirror == 0: local gradients only. */
+    int32_t n_mirror;
+    int32_t reserved0;
+    int64_t mirror_delta[PPOAF_MAX_MIRROR];
 } ppoaf_update_bufs;
 
 size_t ppoaf_update_workspace_bytes(const ppoaf_update_cfg* cfg, int32_t max_batch);

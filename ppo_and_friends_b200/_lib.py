@@ -51,7 +51,8 @@ class UpdateBufs(C.Structure):
                 ("adam_m", C.c_void_p), ("adam_v", C.c_void_p), ("adam_step", C.c_void_p),
                 ("hparams", C.c_void_p), ("epoch_stats", C.c_void_p), ("mb_cursor", C.c_void_p),
                 ("workspace", C.c_void_p), ("workspace_bytes", C.c_size_t), ("n_flat", C.c_int64),
-                ("batch", C.c_int32), ("batch_size", C.c_int32)]
+                ("batch", C.c_int32), ("batch_size", C.c_int32),
+                ("n_mirror", C.c_int32), ("reserved0", C.c_int32), ("mirror_delta", C.c_int64 * 7)]
 
 
 _P = C.c_void_p

@@ -27,7 +27,9 @@ struct GemmGroup {
     // returns the number of sum-of-squares slots (tiles) this problem writes
     int add_backward_w(const float* dZ, const float* X, int ldx, const int64_t* idx, float* dW, float* db, int rows,
                        int in, int out, double* sq_out, bool x_static = false);
-    int launch(const int32_t* cursor, int cursor_stride, cudaStream_t s);
+    // n_mirror / mirror_delta: peer copies of the gradient buffer (ppoaf_update_bufs), applied to backward-w outputs
+    int launch(const int32_t* cursor, int cursor_stride, cudaStream_t s, int n_mirror = 0,
+               const int64_t* mirror_delta = nullptr);
 };
 int backward_w_tiles(int in, int out, int backend);
 void configure_gemm_kernels();
@@ -73,6 +75,8 @@ struct LossArgs {
     float* dz_actor;             // [batch, Ha]  dL/d(pre-activation of the layer below the head)
     float* dz_critic;            // [batch, Hc]
     int Ha, Hc, act;
+    int n_mirror;                // peer copies of d_log_std (push exchange)
+    long long mirror_delta[PPOAF_MAX_MIRROR];
     // optional L2 prefetch of the next minibatch's gathered rows (obs, critic obs); pf_rows[0] == null: off
     const void* pf_rows[2];
     int pf_row_bytes[2];

@@ -495,6 +495,8 @@ __global__ void __launch_bounds__(kLossThreads) ppo_loss_kernel(const LossArgs a
         if (tid >= kLossScalars) {
             const float gls = float(t) * s_dsd[tid - kLossScalars];
             a.d_log_std[tid - kLossScalars] = gls;
+            for (int q = 0; q < a.n_mirror; ++q)
+                *reinterpret_cast<float*>(reinterpret_cast<char*>(a.d_log_std + (tid - kLossScalars)) + a.mirror_delta[q]) = gls;
             my_sq = double(gls) * double(gls);
         }
     }

@@ -67,10 +67,12 @@ int GemmGroup::add_backward_w(const float* dZ, const float* X, int ldx, const in
     return backward_w_tiles(in, out, backend);
 }
 
-int GemmGroup::launch(const int32_t* cursor, int cursor_stride, cudaStream_t s) {
+int GemmGroup::launch(const int32_t* cursor, int cursor_stride, cudaStream_t s, int n_mirror, const int64_t* mirror_delta) {
     if (n_tiles == 0) return 0;
     args->cursor = cursor;
     args->cursor_stride = cursor_stride;
+    args->mirror.n = n_mirror;
+    for (int q = 0; q < n_mirror && q < PPOAF_MAX_MIRROR; ++q) args->mirror.delta[q] = mirror_delta[q];
     if (backend == GEMM_BACKEND_TCGEN05) {
         launch_chain(umma::umma_grouped_gemm_kernel, dim3(n_tiles), dim3(umma::kUThreads + 32), umma::kUmmaSmemBytes, s, *args);
         PPOAF_CHECK_LAUNCH("umma_grouped_gemm_kernel");

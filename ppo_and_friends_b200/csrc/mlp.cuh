@@ -66,11 +66,20 @@ struct GemmProblem {
     int b_static;                   // B is not written by the launch right before this one (and has no gather): it may
                                     //   be staged before the programmatic-dependency wait
 };
+struct MirrorSet {                   // peer copies of the gradient buffer (R > 1 push exchange): byte offsets from
+    int n;                           //   a local gradient address to the same element in every peer's receive slot
+    long long delta[PPOAF_MAX_MIRROR];
+};
+template <typename T>
+__device__ __forceinline__ void mirror_store(const MirrorSet& mir, T* local, const T& v) {
+    for (int q = 0; q < mir.n; ++q) *reinterpret_cast<T*>(reinterpret_cast<char*>(local) + mir.delta[q]) = v;
+}
 struct GroupedGemmArgs {
     int n_problems;
     int cursor_stride;              // idx tables start at (*cursor) * cursor_stride (the minibatch cursor, so
     const int32_t* cursor;          //   one captured graph serves every minibatch); cursor may be null
     GemmProblem p[kMaxGroup];
+    MirrorSet mirror;               // applied to the outputs of EPI_BWD_W problems (dW, db)
 };
 
 constexpr int kBM = 32, kBN = 64, kThreads = 512, kGroups = 16;
@@ -240,7 +249,7 @@ __device__ __forceinline__ float4 load4_guarded(const float* p, int remaining, b
 
 template <bool A_RC, bool B_RC, int VA, int VB, int EPI>
 __device__ __forceinline__ void gemm_tile(const GemmProblem& g, int tile, const int32_t* cursor, int cursor_stride,
-                                          float* smem, uint64_t* bars, int* s_idx) {
+                                          const MirrorSet& mir, float* smem, uint64_t* bars, int* s_idx) {
     const int tid = threadIdx.x;
     PPOAF_STAMP(1);
     const int grp = tid >> 5, lane = tid & 31;
@@ -394,11 +403,16 @@ __device__ __forceinline__ void gemm_tile(const GemmProblem& g, int tile, const 
         }
         float* crow = g.C + int64_t(m) * g.ldc;
         if (g.ldc % 4 == 0 && reinterpret_cast<uintptr_t>(g.C) % 16 == 0 && n + 3 < g.N) {
-            *reinterpret_cast<float4*>(crow + n) = make_float4(o[0], o[1], o[2], o[3]);
+            const float4 o4 = make_float4(o[0], o[1], o[2], o[3]);
+            *reinterpret_cast<float4*>(crow + n) = o4;
+            if constexpr (EPI == EPI_BWD_W) mirror_store(mir, reinterpret_cast<float4*>(crow + n), o4);
         } else {
 #pragma unroll
             for (int j = 0; j < 4; ++j)
-                if (n + j < g.N) crow[n + j] = o[j];
+                if (n + j < g.N) {
+                    crow[n + j] = o[j];
+                    if constexpr (EPI == EPI_BWD_W) mirror_store(mir, crow + n + j, o[j]);
+                }
         }
         if constexpr (EPI == EPI_BWD_W) {
             if (n0 == 0 && c4 == 0 && g.dbias) {
@@ -406,6 +420,7 @@ __device__ __forceinline__ void gemm_tile(const GemmProblem& g, int tile, const 
 #pragma unroll
                 for (int gq = 0; gq < kGroups; ++gq) s += red_b[gq * kBM + r];
                 g.dbias[m] = s;
+                mirror_store(mir, g.dbias + m, s);
                 sq = fmaf(s, s, sq);
             }
         }
@@ -443,7 +458,7 @@ __global__ void __launch_bounds__(kThreads) grouped_gemm_kernel(const GroupedGem
         if (i < args.n_problems && int(blockIdx.x) >= args.p[i].tile_begin) p = i;
     const GemmProblem& g = args.p[p];
     const int tile = int(blockIdx.x) - g.tile_begin;
-#define PPOAF_TILE(ARC, BRC, VA, VB, E) gemm_tile<ARC, BRC, VA, VB, E>(g, tile, args.cursor, args.cursor_stride, smem, s_bars, s_idx)
+#define PPOAF_TILE(ARC, BRC, VA, VB, E) gemm_tile<ARC, BRC, VA, VB, E>(g, tile, args.cursor, args.cursor_stride, args.mirror, smem, s_bars, s_idx)
 #ifdef PPOAF_GEMM_REPEAT   // debug: run the tile twice, the stamps of the second (warm instruction cache) pass survive
 #pragma unroll 1
     for (int rep = 0; rep < 2; ++rep) {

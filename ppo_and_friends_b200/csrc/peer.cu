@@ -2,12 +2,14 @@
 // (replaces: mpi_avg_gradients utils/mpi_utils.py:89-111 + clip_grad_norm_ + Adam.step,
 // policies/ppo_policy.py:1032-1055; on the NCCL path that is all-reduce + norm pass + Adam = 3 launches).
 //
-// Every rank runs this kernel on its own GPU at the same point of the step.  Gradients live in buffers that
-// are mapped into every peer (CUDA IPC over NVSwitch), double-buffered by step parity:
-//   1. cross-GPU barrier: each rank publishes "my gradient buffer for step t is complete" by writing t into
-//      flag[my_rank] of EVERY peer (st.release.sys over NVLink) and spins on its LOCAL flags until all R
+// Every rank runs this kernel on its own GPU at the same point of the step.  Each rank owns a receive buffer
+// [2 step parities][R source ranks][P] mapped into every peer (CUDA IPC over NVSwitch); the backward kernels of
+// rank r PUSH every gradient element into slot [parity][r] of every rank's buffer while they run
+// (ppoaf_update_bufs.mirror_delta), so by the time this kernel starts the gradients have already crossed NVLink:
+//   1. cross-GPU barrier: each rank publishes "my gradients for step t have been written everywhere" by writing t
+//      into flag[my_rank] of EVERY peer (st.release.sys over NVLink) and spins on its LOCAL flags until all R
 //      ranks have published t;
-//   2. one-shot reduce: every thread sums its float4 slots over the R peer buffers in rank order (so every rank
+//   2. one-shot reduce: every thread sums its float4 slots over the R LOCAL slots in rank order (so every rank
 //      gets bit-identical sums), keeps them in registers, and accumulates per-network sums of squares;
 //   3. local grid barrier (all CTAs are co-resident: grid <= #SMs), fixed-order fold of the CTA partials;
 //   4. clip coefficient, bias corrections, Adam on the register-held gradient -> params, m, v (local).
@@ -31,7 +33,7 @@ __device__ long long g_peer_stamps[16];
 #endif
 
 struct PeerArgs {
-    const float* peer_grads[kPeerMaxRanks];   // gradient buffer of every rank for THIS parity (index = rank)
+    const float* peer_grads[kPeerMaxRanks];   // the slot holding rank r's gradients for THIS parity (index = rank)
     uint32_t* peer_flags[kPeerMaxRanks];      // flag array of every rank; element [src_rank] is written by src_rank
     uint32_t* local_flags;                    // == peer_flags[my_rank]
     int n_ranks, my_rank;
@@ -51,13 +53,14 @@ __device__ __forceinline__ uint32_t ld_acquire_gpu(const uint32_t* p) {
     return v;
 }
 
-// ctrl (local, zero-initialised): [0] epoch (cross-GPU barrier value of the last call), [1] local arrive counter,
-// [2] local generation, [3] ticket, [4] error flag
+// ctrl (local, zero-initialised): [0] epoch (barrier value of the last call), [2] grid-barrier "go" word, [3] ticket,
+// [4] error flag;
+// arrive (local, zero-initialised): one word per CTA for the grid barrier
 __global__ void __launch_bounds__(kPeerThreads)
 peer_allreduce_adam_kernel(const PeerArgs pa, float* __restrict__ params, float* __restrict__ m, float* __restrict__ v,
                            int64_t n_actor, int64_t n_total, const double* __restrict__ hp,
                            int64_t* __restrict__ adam_step, int32_t* __restrict__ mb_cursor,
-                           double* __restrict__ partials, uint32_t* __restrict__ ctrl) {
+                           double* __restrict__ partials, uint32_t* __restrict__ arrive, uint32_t* __restrict__ ctrl) {
     __shared__ double s_scr[32];
     __shared__ double s_pw[2];
     __shared__ float s_f[8];
@@ -66,6 +69,20 @@ peer_allreduce_adam_kernel(const PeerArgs pa, float* __restrict__ params, float*
     const int R = pa.n_ranks;
     double* pw = reinterpret_cast<double*>(ctrl + 8);   // cached (t, beta1^t, beta2^t)
     PEER_STAMP(0);
+    // ---- 0. before the dependency wait: parameters and moments (only ever written by this kernel) ----
+    const int64_t nv = n_total / 4, na = n_actor / 4;
+    const int64_t stride = int64_t(gridDim.x) * blockDim.x;
+    float4* p4 = reinterpret_cast<float4*>(params);
+    float4* m4 = reinterpret_cast<float4*>(m);
+    float4* v4 = reinterpret_cast<float4*>(v);
+    float4 P[kPeerMaxVec], M[kPeerMaxVec], V[kPeerMaxVec];
+#pragma unroll
+    for (int k = 0; k < kPeerMaxVec; ++k) {
+        const int64_t i = int64_t(blockIdx.x) * blockDim.x + tid + k * stride;
+        if (i < nv) { P[k] = p4[i]; M[k] = m4[i]; V[k] = v4[i]; }
+    }
+    pdl_wait();                                // the backward pass of this rank has completed: its pushes are out
+    pdl_trigger();
     const uint32_t epoch = ctrl[0] + 1;        // every CTA reads the value of the previous call (updated at the very end)
     if (tid == 0) s_err = 0;
 
@@ -88,8 +105,6 @@ peer_allreduce_adam_kernel(const PeerArgs pa, float* __restrict__ params, float*
 
     PEER_STAMP(1);
     // ---- 2. one-shot reduce in rank order, gradient kept in registers ----
-    const int64_t nv = n_total / 4, na = n_actor / 4;
-    const int64_t stride = int64_t(gridDim.x) * blockDim.x;
     float4 g[kPeerMaxVec];
     double sa = 0.0, sc = 0.0;
 #pragma unroll
@@ -116,20 +131,26 @@ peer_allreduce_adam_kernel(const PeerArgs pa, float* __restrict__ params, float*
     PEER_STAMP(3);
 
     // ---- 3. local grid barrier + fixed-order fold of the CTA partials ----
+    // no contended atomic (148 same-address atomics cost ~4000 clk): CTA b publishes `epoch` in its own arrival word,
+    // the threads of CTA 0 each poll one word and CTA 0 then releases a single "go" word that the others poll
     if (tid == 0) {
         partials[2 * blockIdx.x] = sa;
         partials[2 * blockIdx.x + 1] = sc;
-        __threadfence();
-        const uint32_t gen = ld_acquire_gpu(ctrl + 2);
-        if (atomicAdd(ctrl + 1, 1u) == gridDim.x - 1) {
-            ctrl[1] = 0u;
-            __threadfence();
-            atomicAdd(ctrl + 2, 1u);           // release the generation
-        } else {
+        asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(arrive + blockIdx.x), "r"(epoch) : "memory");
+    }
+    if (blockIdx.x == 0) {
+        if (tid < int(gridDim.x)) {
             const long long t0 = clock64();
-            while (ld_acquire_gpu(ctrl + 2) == gen) {
+            while (int32_t(ld_acquire_gpu(arrive + tid) - epoch) < 0) {
                 if (clock64() - t0 > kSpinLimit) { s_err = 1; break; }
             }
+        }
+        __syncthreads();
+        if (tid == 0 && !s_err) asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(ctrl + 2), "r"(epoch) : "memory");
+    } else if (tid == 0) {
+        const long long t0 = clock64();
+        while (int32_t(ld_acquire_gpu(ctrl + 2) - epoch) < 0) {
+            if (clock64() - t0 > kSpinLimit) { s_err = 1; break; }
         }
     }
     __syncthreads();
@@ -171,15 +192,12 @@ peer_allreduce_adam_kernel(const PeerArgs pa, float* __restrict__ params, float*
     PEER_STAMP(6);
     const float neg_step_size = s_f[0], bc2_sqrt = s_f[1], w1 = s_f[2], beta2 = s_f[3], w2 = s_f[4], eps = s_f[5];
     const float inv_world = float(hp[PPOAF_HP_INV_WORLD]);
-    float4* p4 = reinterpret_cast<float4*>(params);
-    float4* m4 = reinterpret_cast<float4*>(m);
-    float4* v4 = reinterpret_cast<float4*>(v);
 #pragma unroll
     for (int k = 0; k < kPeerMaxVec; ++k) {
         const int64_t i = int64_t(blockIdx.x) * blockDim.x + tid + k * stride;
         if (i >= nv) continue;
         const float coef = i < na ? s_f[6] : s_f[7];
-        float4 pq = p4[i], mq = m4[i], vq = v4[i];
+        const float4 pq = P[k], mq = M[k], vq = V[k];
         float gg[4] = {g[k].x, g[k].y, g[k].z, g[k].w}, p[4] = {pq.x, pq.y, pq.z, pq.w};
         float mm[4] = {mq.x, mq.y, mq.z, mq.w}, vv[4] = {vq.x, vq.y, vq.z, vq.w};
 #pragma unroll
@@ -248,10 +266,11 @@ extern "C" int ppoaf_peer_close(void* p) {
     return 0;
 }
 
-extern "C" size_t ppoaf_peer_ctrl_bytes(void) { return size_t(sm_count()) * 2 * sizeof(double) + 256; }
+static size_t peer_arrive_bytes() { return align_up(size_t(sm_count()) * sizeof(uint32_t), 256); }
+extern "C" size_t ppoaf_peer_ctrl_bytes(void) { return size_t(sm_count()) * 2 * sizeof(double) + peer_arrive_bytes() + 256; }
 
 // peer_grads[r] / peer_flags[r]: pointers valid on THIS device for rank r's buffers (own rank: the local pointers).
-// ctrl: local zero-initialised scratch of ppoaf_peer_ctrl_bytes() bytes (CTA partials, then the barrier words).
+// ctrl: local zero-initialised scratch of ppoaf_peer_ctrl_bytes() bytes (CTA partials | arrival words | control words).
 extern "C" int ppoaf_peer_allreduce_adam(const void* const* peer_grads, void* const* peer_flags, int32_t n_ranks,
                                          int32_t my_rank, float* params, float* adam_m, float* adam_v,
                                          int64_t* adam_step, int32_t* mb_cursor, const double* hparams,
@@ -275,9 +294,11 @@ extern "C" int ppoaf_peer_allreduce_adam(const void* const* peer_grads, void* co
     pa.n_ranks = n_ranks;
     pa.my_rank = my_rank;
     double* partials = static_cast<double*>(ctrl);
-    uint32_t* words = reinterpret_cast<uint32_t*>(static_cast<char*>(ctrl) + size_t(sm_count()) * 2 * sizeof(double));
-    peer_allreduce_adam_kernel<<<grid, kPeerThreads, 0, (cudaStream_t)stream>>>(pa, params, adam_m, adam_v, n_actor, n_total,
-                                                                               hparams, adam_step, mb_cursor, partials, words);
+    uint32_t* arrive = reinterpret_cast<uint32_t*>(static_cast<char*>(ctrl) + size_t(sm_count()) * 2 * sizeof(double));
+    uint32_t* words = reinterpret_cast<uint32_t*>(reinterpret_cast<char*>(arrive) + peer_arrive_bytes());
+    // chained like the single-rank optimizer: the launch before it (last backward GEMM) never writes params / m / v
+    launch_chain(peer_allreduce_adam_kernel, dim3(grid), dim3(kPeerThreads), 0, (cudaStream_t)stream, pa, params, adam_m,
+                 adam_v, n_actor, n_total, hparams, adam_step, mb_cursor, partials, arrive, words);
     PPOAF_CHECK_LAUNCH("peer_allreduce_adam_kernel");
     return 0;
 }

@@ -169,6 +169,7 @@ extern "C" int ppoaf_ppo_minibatch_grads(const ppoaf_update_cfg* cfg, const ppoa
     if (check_cfg(cfg, "ppoaf_ppo_minibatch_grads")) return 1;
     PPOAF_CHECK_ARG(b != nullptr && b->batch >= 1 && b->batch <= b->batch_size && b->n_flat > 0,
                     "ppoaf_ppo_minibatch_grads: bad batch sizes");
+    PPOAF_CHECK_ARG(b->n_mirror >= 0 && b->n_mirror <= PPOAF_MAX_MIRROR, "ppoaf_ppo_minibatch_grads: n_mirror out of range");
     if (b->batch == 1) return 0;  // the reference skips one-row minibatches (ppo.py:2305)
     PPOAF_CHECK_ARG(b->workspace_bytes >= ppoaf_update_workspace_bytes(cfg, b->batch_size),
                     "ppoaf_ppo_minibatch_grads: workspace too small");
@@ -249,6 +250,8 @@ extern "C" int ppoaf_ppo_minibatch_grads(const ppoaf_update_cfg* cfg, const ppoa
     a.pf_row_bytes[0] = cfg->actor.dims[0] * int(sizeof(float));
     a.pf_row_bytes[1] = cfg->critic.dims[0] * int(sizeof(float));
     a.n_flat = b->n_flat;
+    a.n_mirror = b->n_mirror;
+    for (int q = 0; q < b->n_mirror; ++q) a.mirror_delta[q] = b->mirror_delta[q];
     a.fused = fuse_heads ? 1 : 0;
     if (fuse_heads) {
         a.h_actor = sc.actor.act[L[0] - 1];
@@ -291,7 +294,7 @@ extern "C" int ppoaf_ppo_minibatch_grads(const ppoaf_update_cfg* cfg, const ppoa
                                    net[k]->dims[l], net[k]->dims[l + 1], net[k]->activation);
         }
         PPOAF_STEP_LIMIT();
-        if (grp.launch(b->mb_cursor, b->batch_size, s)) return 2;
+        if (grp.launch(b->mb_cursor, b->batch_size, s, b->n_mirror, b->mirror_delta)) return 2;
     }
     return 0;
 }

@@ -167,7 +167,7 @@ __device__ __forceinline__ uint32_t kstep_units() { return RC ? 2u : 64u; }   //
 //   free[s]  : tcgen05.commit                                                     -> stage s may be overwritten
 //   acc      : tcgen05.commit after the last chunk                                 -> accumulator complete
 template <bool A_RC, bool B_RC, int EPI>
-__device__ __forceinline__ void umma_tile(const GemmProblem& g, int tile, int64_t idx_off, float* smem, uint64_t* bars,
+__device__ __forceinline__ void umma_tile(const GemmProblem& g, int tile, int64_t idx_off, const MirrorSet& mir, float* smem, uint64_t* bars,
                                           uint32_t tmem) {
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int m0 = (tile / g.tiles_n) * kUM, n0 = (tile % g.tiles_n) * kUN;
@@ -303,11 +303,16 @@ __device__ __forceinline__ void umma_tile(const GemmProblem& g, int tile, int64_
                 o[j] = v;
             }
             if (vec_out && n + 3 < g.N) {
-                *reinterpret_cast<float4*>(crow + n) = make_float4(o[0], o[1], o[2], o[3]);
+                const float4 o4 = make_float4(o[0], o[1], o[2], o[3]);
+                *reinterpret_cast<float4*>(crow + n) = o4;
+                if constexpr (EPI == EPI_BWD_W) mirror_store(mir, reinterpret_cast<float4*>(crow + n), o4);
             } else {
 #pragma unroll
                 for (int j = 0; j < 4; ++j)
-                    if (n + j < g.N) crow[n + j] = o[j];
+                    if (n + j < g.N) {
+                        crow[n + j] = o[j];
+                        if constexpr (EPI == EPI_BWD_W) mirror_store(mir, crow + n + j, o[j]);
+                    }
             }
         }
     }
@@ -326,7 +331,10 @@ __device__ __forceinline__ void umma_tile(const GemmProblem& g, int tile, int64_
         if (tid < kUM) {
 #pragma unroll
             for (int k = 0; k < kUThreads / 32; ++k) db += red[k * kUM + tid];
-            if (n0 == 0 && g.dbias && m0 + tid < g.M) g.dbias[m0 + tid] = db;
+            if (n0 == 0 && g.dbias && m0 + tid < g.M) {
+                g.dbias[m0 + tid] = db;
+                mirror_store(mir, g.dbias + m0 + tid, db);
+            }
         }
         const double wdb = warp_sum((n0 == 0 && tid < kUM && m0 + tid < g.M) ? double(db) * double(db) : 0.0);
         if (lane == 0) s_sq[warp] = w + wdb;
@@ -376,9 +384,9 @@ __global__ void __launch_bounds__(kUThreads + 32) umma_grouped_gemm_kernel(const
     pdl_trigger();
     const int64_t idx_off = args.cursor ? int64_t(*args.cursor) * args.cursor_stride : 0;
     switch (g.flavour >> 2) {
-        case EPI_FWD:   umma_tile<true, true, EPI_FWD>(g, tile, idx_off, smem, s_bars, tmem); break;
-        case EPI_BWD_X: umma_tile<true, false, EPI_BWD_X>(g, tile, idx_off, smem, s_bars, tmem); break;
-        default:        umma_tile<false, false, EPI_BWD_W>(g, tile, idx_off, smem, s_bars, tmem); break;
+        case EPI_FWD:   umma_tile<true, true, EPI_FWD>(g, tile, idx_off, args.mirror, smem, s_bars, tmem); break;
+        case EPI_BWD_X: umma_tile<true, false, EPI_BWD_X>(g, tile, idx_off, args.mirror, smem, s_bars, tmem); break;
+        default:        umma_tile<false, false, EPI_BWD_W>(g, tile, idx_off, args.mirror, smem, s_bars, tmem); break;
     }
 
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");

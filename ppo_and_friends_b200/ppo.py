@@ -120,6 +120,10 @@ class UpdateEngine:
         b.workspace_bytes = self.workspace.numel() - 256
         b.n_flat = len(ds)
         b.batch, b.batch_size = int(rows), self.batch_size
+        if self.peer is not None:                              # push exchange: mirror every gradient store into the peers
+            b.n_mirror = len(self.peer.mirror_delta)
+            for q, d in enumerate(self.peer.mirror_delta):
+                b.mirror_delta[q] = d
         return b
 
     def _grads(self, bufs):

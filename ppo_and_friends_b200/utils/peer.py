@@ -1,9 +1,12 @@
 """
 NVLink peer-memory group for the fused gradient all-reduce + clip + Adam (csrc/peer.cu).
 
-Each rank allocates two gradient buffers (step parity 0 / 1) and one flag array with cudaMalloc through the
-C ABI, exports CUDA IPC handles, and the handles are exchanged with `torch.distributed.all_gather_object`
-(any backend).  After `PeerGroup(...)` every rank holds device pointers to every peer's buffers.
+Push exchange: each rank allocates ONE receive buffer `[2 parities][R source ranks][n_floats]` and one flag array
+with cudaMalloc through the C ABI, exports CUDA IPC handles, and the handles are exchanged with
+`torch.distributed.all_gather_object` (any backend).  Rank r's backward kernels write every gradient element into
+slot `[parity][r]` of its own buffer AND of every peer's buffer (the `mirror_delta` byte offsets of
+`ppoaf_update_bufs`), so the gradients cross NVLink while the backward pass runs; the fused kernel then only
+exchanges flags and reads its R local slots.
 """
 import ctypes as C
 
@@ -29,10 +32,11 @@ class PeerGroup:
         self.n_floats = int(n_floats)
         self.device = torch.device(device)
         nbytes = (self.n_floats * 4 + 255) // 256 * 256
+        self.slot_bytes = nbytes
         self._local = []
-        for _ in range(3):                                     # grads[0], grads[1], flags
+        for size in (2 * self.world * nbytes, 256):            # receive buffer [2][R][n], flags
             p = C.c_void_p()
-            check(lib.ppoaf_peer_alloc(nbytes if len(self._local) < 2 else 256, C.byref(p)), "ppoaf_peer_alloc")
+            check(lib.ppoaf_peer_alloc(size, C.byref(p)), "ppoaf_peer_alloc")
             self._local.append(p.value)
         handles = []
         for p in self._local:
@@ -43,7 +47,7 @@ class PeerGroup:
         gathered = [None] * self.world
         dist.all_gather_object(gathered, handles)
         self._opened = []
-        self.ptrs = []                                         # ptrs[r] = [grads0, grads1, flags] valid on this device
+        self.ptrs = []                                         # ptrs[r] = [recv, flags] of rank r, valid on this device
         for r in range(self.world):
             if r == self.rank:
                 self.ptrs.append(list(self._local))
@@ -55,13 +59,19 @@ class PeerGroup:
                 mine.append(p.value)
                 self._opened.append(p.value)
             self.ptrs.append(mine)
-        self.grads = [torch.as_tensor(_RawCudaBuffer(self._local[k], self.n_floats), device=self.device) for k in range(2)]
+        def slot(base, parity, src):
+            return base + (parity * self.world + src) * nbytes
+        # this rank's gradient buffer for parity k = its own slot of its own receive buffer
+        self.grads = [torch.as_tensor(_RawCudaBuffer(slot(self._local[0], k, self.rank), self.n_floats), device=self.device)
+                      for k in range(2)]
+        # byte offsets from a local gradient address to the same element of this rank's slot inside every peer
+        self.mirror_delta = [self.ptrs[q][0] - self._local[0] for q in range(self.world) if q != self.rank]
         self.ctrl = torch.zeros(lib.ppoaf_peer_ctrl_bytes(), dtype=torch.uint8, device=self.device)
-        self._grad_arrays = []
+        self._grad_arrays = []                                 # the R LOCAL slots the fused kernel sums, per parity
         for k in range(2):
-            arr = (C.c_void_p * self.world)(*[self.ptrs[r][k] for r in range(self.world)])
+            arr = (C.c_void_p * self.world)(*[slot(self._local[0], k, r) for r in range(self.world)])
             self._grad_arrays.append(arr)
-        self._flag_array = (C.c_void_p * self.world)(*[self.ptrs[r][2] for r in range(self.world)])
+        self._flag_array = (C.c_void_p * self.world)(*[self.ptrs[r][1] for r in range(self.world)])
         dist.barrier()                                         # everyone has mapped everyone before first use
 
     def allreduce_adam(self, parity, nets, mb_cursor, hparams, stream_ptr):
