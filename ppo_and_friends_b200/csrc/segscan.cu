@@ -81,25 +81,34 @@ segscan_kernel(const float* __restrict__ rewards, const float* __restrict__ valu
     __shared__ float s_val[kScanTile + 1];  // values of the tile + 1-element halo (the per-episode tail)
     __shared__ int s_warp_ends[kScanThreads / 32];
     __shared__ Affine2 s_warp_agg[kScanThreads / 32];
-    __shared__ int s_tile;
     __shared__ int s_first_seg;
     __shared__ double s_carry[2];
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    if (tid == 0) s_tile = n_tiles - 1 - atomicAdd(ticket, 1);  // highest tile first: scan runs right to left
-    __syncthreads();
-    const int tile = s_tile;
+    // Highest tile first (the scan runs right to left).  Thread blocks are dispatched in blockIdx order, so every
+    // tile this one looks back at has already been dispatched: no dynamic ticket (4096 same-address atomics cost
+    // ~27 clk each and were most of this kernel's time at 2^22 elements).
+    (void)ticket;
+    const int tile = n_tiles - 1 - int(blockIdx.x);
     const int64_t lo = int64_t(tile) * kScanTile;
     const int64_t hi = min(lo + int64_t(kScanTile), n);
     const int cnt = int(hi - lo);
 
-    if (tid == 32) {  // first segment that intersects the tile: last s with seg_off[s] <= lo
-        int a = 0, b = n_seg;  // invariant: seg_off[a] <= lo < seg_off[b]
+    if (warp == 1) {
+        // first segment that intersects the tile: last s with seg_off[s] <= lo.  A 32-ary search by one warp: every
+        // step probes 32 positions at once, so 115 K segments take 4 dependent global loads instead of 17.
+        int a = 0, b = n_seg;  // invariant: seg_off[a] <= lo < seg_off[b]  (b == n_seg is a virtual +inf)
         while (b - a > 1) {
-            const int m = (a + b) >> 1;
-            if (seg_off[m] <= lo) a = m; else b = m;
+            const int step = (b - a + 31) / 32;
+            const int probe = a + (lane + 1) * step;
+            const bool le = probe < b && seg_off[probe] <= lo;
+            const unsigned m = __ballot_sync(kFull, le);            // monotone: the first k lanes are true
+            const int k = __popc(m);
+            const int na = a + k * step;
+            b = min(b, na + step);
+            a = na;
         }
-        s_first_seg = a;
+        if (lane == 0) s_first_seg = a;
     }
 
     // ---- load (128-bit when the tile is full and aligned, which is every tile but the last) ----

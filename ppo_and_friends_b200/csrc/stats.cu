@@ -9,8 +9,17 @@
 
 namespace ppoaf {
 
-constexpr int kStatRowsPerBlock = 4;   // blockDim.y
-constexpr int kStatUnroll = 4;         // rows in flight per thread
+#ifndef PPOAF_STAT_ROWS
+#define PPOAF_STAT_ROWS 8
+#endif
+#ifndef PPOAF_STAT_UNROLL
+#define PPOAF_STAT_UNROLL 4
+#endif
+#ifndef PPOAF_STAT_GRID_MULT
+#define PPOAF_STAT_GRID_MULT 32
+#endif
+constexpr int kStatRowsPerBlock = PPOAF_STAT_ROWS;   // blockDim.y
+constexpr int kStatUnroll = PPOAF_STAT_UNROLL;       // rows in flight per thread
 constexpr int kMaxFoldWidth = 128;     // narrow rows are folded k-at-a-time up to this many floats
 
 struct FoldPlan {
@@ -42,7 +51,10 @@ static FoldPlan plan_fold(int64_t n_rows, int32_t dim, const void* p) {
     f.bx = (f.vec + 31) / 32 * 32;
     if (f.bx * kStatRowsPerBlock > 1024) return f;  // dim > 1024: generic path
     const int64_t want = ceil_div64(f.rows, int64_t(kStatRowsPerBlock) * kStatUnroll * 8);
-    const int64_t cap = int64_t(sm_count()) * 4;
+#ifndef PPOAF_STAT_GRID_MULT_M
+#define PPOAF_STAT_GRID_MULT_M 4
+#endif
+    const int64_t cap = int64_t(sm_count()) * PPOAF_STAT_GRID_MULT_M;
     f.grid = int(want < 1 ? 1 : (want > cap ? cap : want));
     f.ok = f.rows > 0;
     return f;
@@ -366,7 +378,7 @@ static int launch_normalize(const float* x, int64_t n_rows, int32_t dim, const d
     if (f.ok && reinterpret_cast<uintptr_t>(y) % 16 != 0) f.ok = false;
     if (f.ok) {
         const int64_t want = ceil_div64(f.rows, int64_t(kStatRowsPerBlock) * kStatUnroll * 4);
-        const int64_t cap = int64_t(sm_count()) * 4;
+        const int64_t cap = int64_t(sm_count()) * PPOAF_STAT_GRID_MULT;
         const int grid = int(want < 1 ? 1 : (want > cap ? cap : want));
         normalize_vec_kernel<kDenorm><<<grid, dim3(f.bx, kStatRowsPerBlock), 0, s>>>(
             reinterpret_cast<const float4*>(x), reinterpret_cast<float4*>(y), f.rows, f.vec, dim, state, eps, lo, hi);
