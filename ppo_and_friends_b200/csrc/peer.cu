@@ -227,6 +227,225 @@ peer_allreduce_adam_kernel(const PeerArgs pa, float* __restrict__ params, float*
     }
 }
 
+
+// =====================================================================================================================
+// NVLS variant (NVSwitch multicast): two-shot all-reduce fused with clip + Adam, ZeRO-style ownership.
+// The gradient buffers, a parameter staging buffer and a small flag block live in SYMMETRIC memory (same layout on
+// every rank, mapped by torch.distributed._symmetric_memory; `*_mc` are multicast addresses of the same buffers).
+// Rank r owns slice r of the flat parameter vector:
+//   1. cross-GPU barrier (gradients of step t are complete everywhere);
+//   2. multimem.ld_reduce over the owned slice: the switch returns the sum over all R replicas, every element is
+//      reduced exactly once (by its owner), so all ranks end up with bit-identical parameters by construction;
+//   3. slice sums of squares -> exchanged through the flag block (second barrier) -> identical norms everywhere;
+//   4. clip + Adam on the owned slice (m, v are only maintained for the owned slice), new parameters are broadcast
+//      with multimem.st into every rank's staging buffer;
+//   5. third barrier, then every rank copies the staging buffer into its parameters.
+// Per step and rank this moves ~2 x 4 B/parameter over NVLink regardless of R (the push exchange moves (R-1) x 4 B).
+struct NvlsArgs {
+    const float* g_mc;                        // multicast address of the gradient buffer of THIS parity
+    float* s_mc;                              // multicast address of the parameter staging buffer
+    const float* s_local;                     // this rank's staging buffer
+    uint32_t* blk_peer[kPeerMaxRanks];        // flag block of rank r (mapped): u32 flags[3][8] | double part[8][2]
+    uint32_t* blk_local;
+    int n_ranks, my_rank;
+};
+constexpr int kNvlsPartOff = 128 / 4;         // offset of the partial-sum slots inside a flag block, in u32 words
+
+__device__ __forceinline__ float4 multimem_ld_reduce_f4(const float* mc) {
+    float4 r;
+    asm volatile("multimem.ld_reduce.relaxed.sys.global.add.v4.f32 {%0,%1,%2,%3}, [%4];"
+                 : "=f"(r.x), "=f"(r.y), "=f"(r.z), "=f"(r.w) : "l"(mc) : "memory");
+    return r;
+}
+__device__ __forceinline__ void multimem_st_f4(float* mc, const float4& v) {
+    asm volatile("multimem.st.relaxed.sys.global.v4.f32 [%0], {%1,%2,%3,%4};" ::"l"(mc), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w)
+                 : "memory");
+}
+// every thread tid < R of the calling CTA polls one LOCAL flag word until it reaches `epoch`
+__device__ __forceinline__ void xgpu_wait(const uint32_t* flags, int R, uint32_t epoch, int tid, int* s_err) {
+    if (tid < R) {
+        const long long t0 = clock64();
+        while (int32_t(ld_acquire_sys(flags + tid) - epoch) < 0) {
+            if (clock64() - t0 > kSpinLimit) { *s_err = 1; break; }
+        }
+    }
+    __syncthreads();
+}
+// CTA b announces `epoch` in its arrival word; CTA 0 waits for all of them (its threads poll one word each)
+__device__ __forceinline__ void gather_to_cta0(uint32_t* arrive, uint32_t epoch, int tid, int* s_err) {
+    __syncthreads();
+    if (tid == 0) asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(arrive + blockIdx.x), "r"(epoch) : "memory");
+    if (blockIdx.x == 0) {
+        if (tid < int(gridDim.x)) {
+            const long long t0 = clock64();
+            while (int32_t(ld_acquire_gpu(arrive + tid) - epoch) < 0) {
+                if (clock64() - t0 > kSpinLimit) { *s_err = 1; break; }
+            }
+        }
+        __syncthreads();
+    }
+}
+
+// ctrl (local, zero-initialised): [0] epoch, [3] ticket, [4] error flag, [8..] cached beta powers
+// arrive: 2 x gridDim.x local words; partials: 2 doubles per CTA
+__global__ void __launch_bounds__(kPeerThreads)
+nvls_allreduce_adam_kernel(const NvlsArgs pa, float* __restrict__ params, float* __restrict__ m, float* __restrict__ v,
+                           int64_t n_actor, int64_t n_total, const double* __restrict__ hp,
+                           int64_t* __restrict__ adam_step, int32_t* __restrict__ mb_cursor,
+                           double* __restrict__ partials, uint32_t* __restrict__ arrive, uint32_t* __restrict__ ctrl) {
+    __shared__ double s_scr[32];
+    __shared__ double s_pw[2];
+    __shared__ double s_tot[2];
+    __shared__ float s_f[8];
+    __shared__ int s_err;
+    const int tid = threadIdx.x;
+    const int R = pa.n_ranks, me = pa.my_rank;
+    double* pw = reinterpret_cast<double*>(ctrl + 8);
+    const int64_t nv = n_total / 4, na = n_actor / 4;
+    const int64_t slice = (nv + R - 1) / R;
+    const int64_t s_lo = int64_t(me) * slice, s_hi = min(nv, s_lo + slice);
+    const int64_t gstride = int64_t(gridDim.x) * blockDim.x;
+    const int64_t gtid = int64_t(blockIdx.x) * blockDim.x + tid;
+    float4* p4 = reinterpret_cast<float4*>(params);
+    float4* m4 = reinterpret_cast<float4*>(m);
+    float4* v4 = reinterpret_cast<float4*>(v);
+
+    // ---- 0. before the dependency wait: parameters and moments of the owned slice ----
+    float4 P[kPeerMaxVec], M[kPeerMaxVec], V[kPeerMaxVec], g[kPeerMaxVec];
+#pragma unroll
+    for (int k = 0; k < kPeerMaxVec; ++k) {
+        const int64_t i = s_lo + gtid + k * gstride;
+        if (i < s_hi) { P[k] = p4[i]; M[k] = m4[i]; V[k] = v4[i]; }
+    }
+    pdl_wait();
+    pdl_trigger();
+    const uint32_t epoch = ctrl[0] + 1;
+    if (tid == 0) s_err = 0;
+    __syncthreads();
+
+    // ---- 1. cross-GPU barrier: everyone's gradients of this step are complete ----
+    if (blockIdx.x == 0 && tid < R) {
+        __threadfence_system();
+        st_release_sys(pa.blk_peer[tid] + 0 * 8 + me, epoch);
+    }
+    xgpu_wait(pa.blk_local + 0 * 8, R, epoch, tid, &s_err);
+    if (s_err) { if (tid == 0) atomicExch(ctrl + 4, 1u); return; }
+
+    // ---- 2. in-switch reduction of the owned slice ----
+    double sa = 0.0, sc = 0.0;
+#pragma unroll
+    for (int k = 0; k < kPeerMaxVec; ++k) {
+        const int64_t i = s_lo + gtid + k * gstride;
+        g[k] = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (i < s_hi) {
+            g[k] = multimem_ld_reduce_f4(pa.g_mc + 4 * i);
+            const float q = fmaf(g[k].x, g[k].x, fmaf(g[k].y, g[k].y, fmaf(g[k].z, g[k].z, g[k].w * g[k].w)));
+            if (i < na) sa += double(q); else sc += double(q);
+        }
+    }
+    sa = block_sum(sa, s_scr);
+    sc = block_sum(sc, s_scr);
+    if (tid == 0) { partials[2 * blockIdx.x] = sa; partials[2 * blockIdx.x + 1] = sc; }
+
+    // ---- 3. slice sums -> every rank (CTA 0 folds the CTA partials and writes them into every peer's flag block) ----
+    gather_to_cta0(arrive, epoch, tid, &s_err);
+    if (blockIdx.x == 0) {
+        double ta = 0.0, tc = 0.0;
+        for (int b = tid; b < int(gridDim.x); b += blockDim.x) { ta += __ldcg(&partials[2 * b]); tc += __ldcg(&partials[2 * b + 1]); }
+        ta = block_sum(ta, s_scr);
+        tc = block_sum(tc, s_scr);
+        if (tid < R) {
+            double* slot = reinterpret_cast<double*>(pa.blk_peer[tid] + kNvlsPartOff) + 2 * me;
+            asm volatile("st.relaxed.sys.global.f64 [%0], %1;" ::"l"(slot), "d"(ta) : "memory");
+            asm volatile("st.relaxed.sys.global.f64 [%0], %1;" ::"l"(slot + 1), "d"(tc) : "memory");
+            st_release_sys(pa.blk_peer[tid] + 1 * 8 + me, epoch);
+        }
+    }
+    xgpu_wait(pa.blk_local + 1 * 8, R, epoch, tid, &s_err);
+    if (s_err) { if (tid == 0) atomicExch(ctrl + 4, 2u); return; }
+    if (tid == 0) {
+        const double* part = reinterpret_cast<const double*>(pa.blk_local + kNvlsPartOff);
+        double ta = 0.0, tc = 0.0;
+        for (int r = 0; r < R; ++r) {                  // rank order: identical everywhere
+            double xa, xc;
+            asm volatile("ld.relaxed.sys.global.f64 %0, [%1];" : "=d"(xa) : "l"(part + 2 * r) : "memory");
+            asm volatile("ld.relaxed.sys.global.f64 %0, [%1];" : "=d"(xc) : "l"(part + 2 * r + 1) : "memory");
+            ta += xa; tc += xc;
+        }
+        s_tot[0] = ta; s_tot[1] = tc;
+    }
+    __syncthreads();
+
+    // ---- 4. scalars, Adam on the owned slice, broadcast of the new parameters ----
+    const int64_t t = *adam_step + 1;
+    const float inv_world = float(hp[PPOAF_HP_INV_WORLD]);
+    if (tid == 0) {
+        const float max_norm = float(hp[PPOAF_HP_GRAD_CLIP]);
+        float ca = 1.f, cc = 1.f;
+        if (max_norm >= 0.f) {
+            ca = fminf(max_norm / (float(sqrt(s_tot[0]) * double(inv_world)) + 1e-6f), 1.f);
+            cc = fminf(max_norm / (float(sqrt(s_tot[1]) * double(inv_world)) + 1e-6f), 1.f);
+        }
+        const double b1d = hp[PPOAF_HP_BETA1], b2d = hp[PPOAF_HP_BETA2];
+        double p1, p2;
+        beta_powers(pw, t, b1d, b2d, p1, p2);
+        s_pw[0] = p1; s_pw[1] = p2;
+        s_f[0] = float(-(hp[PPOAF_HP_LR] / (1.0 - p1)));
+        s_f[1] = float(sqrt(1.0 - p2));
+        s_f[2] = float(1.0 - b1d);
+        s_f[3] = float(b2d);
+        s_f[4] = float(1.0 - b2d);
+        s_f[5] = float(hp[PPOAF_HP_ADAM_EPS]);
+        s_f[6] = ca;
+        s_f[7] = cc;
+    }
+    __syncthreads();
+    const float neg_step_size = s_f[0], bc2_sqrt = s_f[1], w1 = s_f[2], beta2 = s_f[3], w2 = s_f[4], eps = s_f[5];
+#pragma unroll
+    for (int k = 0; k < kPeerMaxVec; ++k) {
+        const int64_t i = s_lo + gtid + k * gstride;
+        if (i >= s_hi) continue;
+        const float coef = i < na ? s_f[6] : s_f[7];
+        float gg[4] = {g[k].x, g[k].y, g[k].z, g[k].w}, p[4] = {P[k].x, P[k].y, P[k].z, P[k].w};
+        float mm[4] = {M[k].x, M[k].y, M[k].z, M[k].w}, vv[4] = {V[k].x, V[k].y, V[k].z, V[k].w};
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {          // same operation order as adam_update_kernel / torch's CPU kernels
+            const float gk = __fmul_rn(__fmul_rn(gg[j], inv_world), coef);
+            mm[j] = __fadd_rn(mm[j], __fmul_rn(w1, __fsub_rn(gk, mm[j])));
+            vv[j] = __fadd_rn(__fmul_rn(vv[j], beta2), __fmul_rn(__fmul_rn(w2, gk), gk));
+            const float denom = __fadd_rn(__fdiv_rn(__fsqrt_rn(vv[j]), bc2_sqrt), eps);
+            p[j] = __fadd_rn(p[j], __fdiv_rn(__fmul_rn(neg_step_size, mm[j]), denom));
+        }
+        m4[i] = make_float4(mm[0], mm[1], mm[2], mm[3]);
+        v4[i] = make_float4(vv[0], vv[1], vv[2], vv[3]);
+        multimem_st_f4(pa.s_mc + 4 * i, make_float4(p[0], p[1], p[2], p[3]));
+    }
+    __threadfence_system();                    // this thread's broadcast stores are ordered before the flags below
+
+    // ---- 5. third barrier: every rank's slice has landed in every staging buffer ----
+    gather_to_cta0(arrive + gridDim.x, epoch, tid, &s_err);
+    if (blockIdx.x == 0 && tid < R) {
+        __threadfence_system();
+        st_release_sys(pa.blk_peer[tid] + 2 * 8 + me, epoch);
+    }
+    xgpu_wait(pa.blk_local + 2 * 8, R, epoch, tid, &s_err);
+    if (s_err) { if (tid == 0) atomicExch(ctrl + 4, 3u); return; }
+    for (int64_t i = gtid; i < nv; i += gstride) p4[i] = __ldcg(reinterpret_cast<const float4*>(pa.s_local) + i);
+
+    // ---- the last CTA to finish advances the counters ----
+    __syncthreads();
+    if (tid == 0) {
+        __threadfence();
+        if (atomicAdd(ctrl + 3, 1u) == gridDim.x - 1) {
+            *adam_step = t;
+            if (mb_cursor) *mb_cursor += 1;
+            pw[0] = double(t); pw[1] = s_pw[0]; pw[2] = s_pw[1];
+            ctrl[0] = epoch;
+            ctrl[3] = 0u;
+        }
+    }
+}
+
 }  // namespace ppoaf
 
 using namespace ppoaf;
@@ -308,3 +527,44 @@ extern "C" int ppoaf_debug_peer_stamps(long long* out_host) {
     return cudaMemcpyFromSymbol(out_host, ppoaf::g_peer_stamps, sizeof(long long) * 16) == cudaSuccess ? 0 : 1;
 }
 #endif
+
+// ---- NVLS variant ------------------------------------------------------------------------------------------------
+extern "C" size_t ppoaf_nvls_ctrl_bytes(void) {
+    return size_t(sm_count()) * 2 * sizeof(double) + 2 * peer_arrive_bytes() + 256;
+}
+extern "C" size_t ppoaf_nvls_flag_block_bytes(void) { return 256; }
+
+// g_mc / s_mc: multicast addresses of this parity's gradient buffer and of the parameter staging buffer;
+// s_local: this rank's staging buffer; flag_blocks[r]: rank r's zero-initialised flag block mapped on this device
+// (ppoaf_nvls_flag_block_bytes() bytes, symmetric memory); ctrl: local zeroed scratch of ppoaf_nvls_ctrl_bytes().
+extern "C" int ppoaf_nvls_allreduce_adam(const float* g_mc, float* s_mc, const float* s_local, void* const* flag_blocks,
+                                         int32_t n_ranks, int32_t my_rank, float* params, float* adam_m, float* adam_v,
+                                         int64_t* adam_step, int32_t* mb_cursor, const double* hparams, int64_t n_actor,
+                                         int64_t n_critic, void* ctrl, void* stream) {
+    PPOAF_CHECK_ARG(n_ranks >= 2 && n_ranks <= kPeerMaxRanks && my_rank >= 0 && my_rank < n_ranks,
+                    "ppoaf_nvls_allreduce_adam: 2..%d ranks", kPeerMaxRanks);
+    PPOAF_CHECK_ARG(n_actor % 4 == 0 && n_critic % 4 == 0, "ppoaf_nvls_allreduce_adam: segments must be multiples of 4 floats");
+    PPOAF_CHECK_ARG(g_mc && s_mc && s_local, "ppoaf_nvls_allreduce_adam: null multicast pointers");
+    const int64_t n_total = n_actor + n_critic;
+    const int64_t nv = n_total / 4;
+    const int64_t slice = (nv + n_ranks - 1) / n_ranks;
+    int grid = sm_count();
+    const int64_t need = ceil_div64(slice, kPeerThreads);
+    if (need < grid) grid = int(need < 1 ? 1 : need);
+    PPOAF_CHECK_ARG(slice <= int64_t(grid) * kPeerThreads * kPeerMaxVec,
+                    "ppoaf_nvls_allreduce_adam: %lld parameters exceed the register-resident limit", (long long)n_total);
+    NvlsArgs pa{};
+    pa.g_mc = g_mc; pa.s_mc = s_mc; pa.s_local = s_local;
+    for (int r = 0; r < n_ranks; ++r) pa.blk_peer[r] = static_cast<uint32_t*>(flag_blocks[r]);
+    pa.blk_local = static_cast<uint32_t*>(flag_blocks[my_rank]);
+    pa.n_ranks = n_ranks; pa.my_rank = my_rank;
+    double* partials = static_cast<double*>(ctrl);
+    uint32_t* arrive = reinterpret_cast<uint32_t*>(static_cast<char*>(ctrl) + size_t(sm_count()) * 2 * sizeof(double));
+    uint32_t* words = reinterpret_cast<uint32_t*>(reinterpret_cast<char*>(arrive) + 2 * peer_arrive_bytes());
+    // arrive is used as two arrays of gridDim.x words: the second one starts at arrive + grid
+    launch_chain(nvls_allreduce_adam_kernel, dim3(grid), dim3(kPeerThreads), 0, (cudaStream_t)stream, pa, params, adam_m,
+                 adam_v, n_actor, n_total, hparams, adam_step, mb_cursor, partials, arrive, words);
+    PPOAF_CHECK_LAUNCH("nvls_allreduce_adam_kernel");
+    return 0;
+}
+

@@ -72,6 +72,14 @@ constexpr int kScanThreads = 128;
 constexpr int kScanItems = 8;
 constexpr int kScanTile = kScanThreads * kScanItems;  // 1024 timesteps per CTA
 
+#ifdef PPOAF_GEMM_TIMING
+__device__ unsigned long long g_scan_times[4 * 8192];
+__device__ __forceinline__ unsigned long long gtimer() { unsigned long long t; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t)); return t; }
+#define SCAN_T(k) do { if (threadIdx.x == 0 && blockIdx.x < 8192) g_scan_times[4 * blockIdx.x + (k)] = gtimer(); } while (0)
+#else
+#define SCAN_T(k) do {} while (0)
+#endif
+
 __global__ void __launch_bounds__(kScanThreads, 8)
 segscan_kernel(const float* __restrict__ rewards, const float* __restrict__ values,
                const uint8_t* __restrict__ seg_flag, const int64_t* __restrict__ seg_off,
@@ -89,6 +97,7 @@ segscan_kernel(const float* __restrict__ rewards, const float* __restrict__ valu
     // tile this one looks back at has already been dispatched: no dynamic ticket (4096 same-address atomics cost
     // ~27 clk each and were most of this kernel's time at 2^22 elements).
     (void)ticket;
+    SCAN_T(0);
     const int tile = n_tiles - 1 - int(blockIdx.x);
     const int64_t lo = int64_t(tile) * kScanTile;
     const int64_t hi = min(lo + int64_t(kScanTile), n);
@@ -214,6 +223,7 @@ segscan_kernel(const float* __restrict__ rewards, const float* __restrict__ valu
         Affine2 tile_agg = s_warp_agg[0];
         for (int w = 1; w < kScanThreads / 32; ++w) tile_agg = compose(tile_agg, s_warp_agg[w]);
         TileDesc* d = desc + tile;
+        SCAN_T(1);
         const bool closed = (tile_agg.bA == 0.0 && tile_agg.bR == 0.0) || tile == n_tiles - 1;
         d->aA = tile_agg.aA; d->bA = tile_agg.bA; d->aR = tile_agg.aR; d->bR = tile_agg.bR;
         if (closed) {  // carry-in cannot matter (or is zero past the end): value known at once
@@ -256,6 +266,7 @@ segscan_kernel(const float* __restrict__ rewards, const float* __restrict__ valu
     }
     __syncthreads();
 
+    SCAN_T(2);
     // ---- apply: values right of this thread, then walk the thread's items right to left ----
     double xA = fma(right_in_tile.bA, s_carry[0], right_in_tile.aA);
     double xR = fma(right_in_tile.bR, s_carry[1], right_in_tile.aR);
@@ -283,9 +294,16 @@ segscan_kernel(const float* __restrict__ rewards, const float* __restrict__ valu
                 rtg_out[lo + i0 + k] = og[k];
             }
     }
+    SCAN_T(3);
 }
 
 }  // namespace ppoaf
+
+#ifdef PPOAF_GEMM_TIMING
+extern "C" int ppoaf_debug_scan_times(unsigned long long* out_host, int n) {
+    return cudaMemcpyFromSymbol(out_host, ppoaf::g_scan_times, sizeof(unsigned long long) * 4 * n) == cudaSuccess ? 0 : 1;
+}
+#endif
 
 using namespace ppoaf;
 

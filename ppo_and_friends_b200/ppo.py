@@ -59,8 +59,8 @@ class UpdateEngine:
         self.peer = None
         self.step_parity = 0
         if mpi_utils.get_num_procs() > 1 and os.environ.get("PPOAF_PEER", "1") != "0" and self.device.type == "cuda":
-            from .utils.peer import PeerGroup
-            self.peer = PeerGroup(policy.nets.n_actor + policy.nets.n_critic, self.device)
+            from .utils.peer import make_exchange_group
+            self.peer = make_exchange_group(policy.nets.n_actor + policy.nets.n_critic, self.device)
         nets = policy.nets
         cfg = _lib.UpdateCfg()
         cfg.actor, cfg.critic = nets.actor.desc, nets.critic.desc

@@ -95,3 +95,85 @@ class PeerGroup:
         for p in self._local:
             lib.ppoaf_peer_free(C.c_void_p(p))
         self._opened, self._local = [], []
+
+
+class NvlsGroup:
+    """
+    NVSwitch-multicast variant (csrc/peer.cu, nvls_allreduce_adam_kernel): the gradient buffers (two parities), a
+    parameter staging buffer and a 256-byte flag block are ONE symmetric allocation made with
+    `torch.distributed._symmetric_memory` (plumbing: VMM allocation, handle exchange, multicast binding).  Same interface
+    as PeerGroup; `mirror_delta` is empty because nothing is pushed by the backward kernels.
+    """
+
+    @staticmethod
+    def available():
+        try:
+            import torch.distributed._symmetric_memory  # noqa: F401
+            return True
+        except Exception:
+            return False
+
+    def __init__(self, n_floats, device):
+        import torch.distributed._symmetric_memory as symm_mem
+        assert dist.is_initialized() and dist.get_world_size() > 1
+        lib = load()
+        self.rank, self.world = dist.get_rank(), dist.get_world_size()
+        self.n_floats = int(n_floats)
+        self.device = torch.device(device)
+        slot = (self.n_floats * 4 + 255) // 256 * 256 // 4          # floats per buffer, 256-byte aligned
+        blk = lib.ppoaf_nvls_flag_block_bytes() // 4
+        self._buf = symm_mem.empty(3 * slot + blk, dtype=torch.float32, device=self.device)
+        self._buf.zero_()
+        torch.cuda.synchronize(self.device)
+        self._hdl = symm_mem.rendezvous(self._buf, group=dist.group.WORLD)
+        mc = int(getattr(self._hdl, "multicast_ptr", 0) or 0)
+        if mc == 0:
+            raise RuntimeError("symmetric memory has no multicast mapping on this system")
+        base = self._buf.data_ptr()
+        self.grads = [self._buf[k * slot:k * slot + self.n_floats] for k in range(2)]
+        self.mirror_delta = []
+        self._g_mc = [mc + k * slot * 4 for k in range(2)]
+        self._s_mc = mc + 2 * slot * 4
+        self._s_local = base + 2 * slot * 4
+        peers = [int(p) for p in self._hdl.buffer_ptrs]
+        self._blocks = (C.c_void_p * self.world)(*[peers[r] + 3 * slot * 4 for r in range(self.world)])
+        self._ctrl_bytes = lib.ppoaf_nvls_ctrl_bytes()
+        self.ctrl = torch.zeros(self._ctrl_bytes, dtype=torch.uint8, device=self.device)
+        dist.barrier()
+
+    def allreduce_adam(self, parity, nets, mb_cursor, hparams, stream_ptr):
+        check(load().ppoaf_nvls_allreduce_adam(
+            C.c_void_p(self._g_mc[parity]), C.c_void_p(self._s_mc), C.c_void_p(self._s_local), self._blocks, self.world,
+            self.rank, C.c_void_p(nets.flat_params.data_ptr()), C.c_void_p(nets.adam_m.data_ptr()),
+            C.c_void_p(nets.adam_v.data_ptr()), C.c_void_p(nets.adam_step.data_ptr()), C.c_void_p(mb_cursor.data_ptr()),
+            C.c_void_p(hparams.data_ptr()), nets.n_actor, nets.n_critic, C.c_void_p(self.ctrl.data_ptr()), stream_ptr),
+            "ppoaf_nvls_allreduce_adam")
+
+    def error_flag(self):
+        off = self._ctrl_bytes - 256 + 16
+        return int(self.ctrl[off:off + 4].view(torch.int32).item())
+
+    def close(self):
+        torch.cuda.synchronize(self.device)
+        if dist.is_initialized():
+            dist.barrier()
+        self._hdl = None
+        self._buf = None
+
+
+def make_exchange_group(n_floats, device):
+    """NVLS (multicast) when the system offers it and PPOAF_NVLS != 0, else the push exchange over CUDA IPC."""
+    import os
+    if os.environ.get("PPOAF_NVLS", "1") != "0" and NvlsGroup.available():
+        ok = torch.zeros(1, dtype=torch.int32, device=device)
+        grp = None
+        try:
+            grp = NvlsGroup(n_floats, device)
+            ok += 1
+        except Exception as e:                              # no multicast / no VMM support: every rank must agree
+            if dist.get_rank() == 0:
+                print(f"NVLS exchange unavailable ({type(e).__name__}: {e}); using the push exchange", flush=True)
+        dist.all_reduce(ok, op=dist.ReduceOp.MIN)
+        if int(ok.item()) == 1:
+            return grp
+    return PeerGroup(n_floats, device)

@@ -50,6 +50,10 @@ def main():
     torch.manual_seed(77 + rank)                    # the reference seeds rank r with seed + r
     ppo_batch_train(state, _Loader(ds, 64), "pol")
     stage("epoch done")
+    expect = os.environ.get("PPOAF_MG_EXPECT")     # the exchange the test asked for must be the one that ran
+    if expect:
+        got = {"NvlsGroup": "nvls", "PeerGroup": "push", "NoneType": "nccl"}[type(pol._engine.peer).__name__]
+        assert got == expect, f"expected the {expect} exchange, the engine chose {got}"
     perm = pol._engine._perm_dev.cpu().numpy()
     gathered = [None] * world
     dist.all_gather_object(gathered, dict(host=host, perm=perm))

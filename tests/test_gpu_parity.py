@@ -395,15 +395,17 @@ def test_update_vs_oracle_humanoid_shape(gemm_backend):
 
 # ----------------------------------------------------------------------------------------- P5 / multi-GPU
 @pytest.mark.parametrize("discrete", [False, True])
-@pytest.mark.parametrize("peer", ["1", "0"])
+@pytest.mark.parametrize("peer", ["nvls", "push", "nccl"])
 def test_two_rank_update_matches_multirank_oracle(discrete, peer):
-    """DD-PPO step on 2 GPUs against the multi-rank oracle: peer="1" = fused NVLink all-reduce + clip + Adam
-    kernel (csrc/peer.cu), peer="0" = NCCL all-reduce + norm pass + Adam."""
+    """DD-PPO step on 2 GPUs against the multi-rank oracle.  nvls = NVSwitch-multicast two-shot all-reduce fused with
+    clip + Adam, push = gradients pushed over NVLink peer memory by the backward kernels + fused all-reduce + clip +
+    Adam (both csrc/peer.cu), nccl = NCCL all-reduce + norm pass + Adam."""
     import os, subprocess, sys
     if torch.cuda.device_count() < 2:
         pytest.skip("needs 2 GPUs")
     root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-    env = dict(os.environ, PPOAF_MG_DISCRETE="1" if discrete else "0", PPOAF_PEER=peer)
+    env = dict(os.environ, PPOAF_MG_DISCRETE="1" if discrete else "0", PPOAF_PEER="0" if peer == "nccl" else "1",
+               PPOAF_NVLS="1" if peer == "nvls" else "0", PPOAF_MG_EXPECT=peer)
     port = 29500 + os.getpid() % 1000
     res = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2",
                           "--master-addr", "127.0.0.1", "--master-port", str(port),
