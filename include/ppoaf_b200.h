@@ -249,11 +249,12 @@ int    ppoaf_peer_allreduce_adam(const void* const* peer_grads, void* const* pee
  * staging buffer and one flag block per rank live in SYMMETRIC memory (torch.distributed._symmetric_memory provides the
  * peer and multicast mappings).  Rank r owns slice r of the flat parameters: multimem.ld_reduce returns the in-switch
  * sum of its slice, the slice norms are exchanged through the flag blocks, the owner applies clip + Adam (m, v are only
- * maintained for the owned slice) and broadcasts the new parameters with multimem.st; every rank then copies the staging
- * buffer into `params`.  ~2 x 4 B/parameter of NVLink traffic per rank and step, independent of R. */
+ * maintained for the owned slice) and stores the new parameters in its staging buffer; every rank then gathers all slices
+ * from their owners' staging buffers (staging[r], peer mappings).  ~2 x 4 B/parameter of NVLink traffic per rank and
+ * step, independent of R. */
 size_t ppoaf_nvls_ctrl_bytes(void);
 size_t ppoaf_nvls_flag_block_bytes(void);
-int    ppoaf_nvls_allreduce_adam(const float* g_mc, float* s_mc, const float* s_local, void* const* flag_blocks,
+int    ppoaf_nvls_allreduce_adam(const float* g_mc, void* const* staging, void* const* flag_blocks,
                                  int32_t n_ranks, int32_t my_rank, float* params, float* adam_m, float* adam_v,
                                  int64_t* adam_step, int32_t* mb_cursor, const double* hparams, int64_t n_actor,
                                  int64_t n_critic, void* ctrl, void* stream);

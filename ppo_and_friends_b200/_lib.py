@@ -84,8 +84,8 @@ _SIGNATURES = {
     "ppoaf_head_evaluate": (C.c_int, [C.c_int32, _P, C.c_int32, _P, C.c_float, _P, C.c_int32, C.c_int32, _P, _P, _P]),
     "ppoaf_nvls_ctrl_bytes": (C.c_size_t, []),
     "ppoaf_nvls_flag_block_bytes": (C.c_size_t, []),
-    "ppoaf_nvls_allreduce_adam": (C.c_int, [_P, _P, _P, C.POINTER(C.c_void_p), C.c_int32, C.c_int32, _P, _P, _P, _P, _P, _P,
-                                            C.c_int64, C.c_int64, _P, _P]),
+    "ppoaf_nvls_allreduce_adam": (C.c_int, [_P, C.POINTER(C.c_void_p), C.POINTER(C.c_void_p), C.c_int32, C.c_int32, _P, _P, _P,
+                                            _P, _P, _P, C.c_int64, C.c_int64, _P, _P]),
     "ppoaf_peer_alloc": (C.c_int, [C.c_size_t, C.POINTER(C.c_void_p)]),
     "ppoaf_peer_free": (C.c_int, [_P]),
     "ppoaf_peer_export": (C.c_int, [_P, C.c_char_p]),

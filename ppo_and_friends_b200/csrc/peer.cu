@@ -237,14 +237,14 @@ peer_allreduce_adam_kernel(const PeerArgs pa, float* __restrict__ params, float*
 //   2. multimem.ld_reduce over the owned slice: the switch returns the sum over all R replicas, every element is
 //      reduced exactly once (by its owner), so all ranks end up with bit-identical parameters by construction;
 //   3. slice sums of squares -> exchanged through the flag block (second barrier) -> identical norms everywhere;
-//   4. clip + Adam on the owned slice (m, v are only maintained for the owned slice), new parameters are broadcast
-//      with multimem.st into every rank's staging buffer;
-//   5. third barrier, then every rank copies the staging buffer into its parameters.
+//   4. clip + Adam on the owned slice (m, v are only maintained for the owned slice), new parameters go to the owner's
+//      staging buffer (a multimem.st broadcast was measured slower: its system fence costs ~10 us);
+//   5. third barrier, then every rank gathers all slices from their owners' staging buffers over NVLink.
 // Per step and rank this moves ~2 x 4 B/parameter over NVLink regardless of R (the push exchange moves (R-1) x 4 B).
 struct NvlsArgs {
     const float* g_mc;                        // multicast address of the gradient buffer of THIS parity
-    float* s_mc;                              // multicast address of the parameter staging buffer
-    const float* s_local;                     // this rank's staging buffer
+    float* s_local;                           // this rank's parameter staging buffer (holds its own slice)
+    const float* s_peer[kPeerMaxRanks];       // staging buffer of rank r (mapped)
     uint32_t* blk_peer[kPeerMaxRanks];        // flag block of rank r (mapped): u32 flags[3][8] | double part[8][2]
     uint32_t* blk_local;
     int n_ranks, my_rank;
@@ -272,9 +272,14 @@ __device__ __forceinline__ void xgpu_wait(const uint32_t* flags, int R, uint32_t
     __syncthreads();
 }
 // CTA b announces `epoch` in its arrival word; CTA 0 waits for all of them (its threads poll one word each)
-__device__ __forceinline__ void gather_to_cta0(uint32_t* arrive, uint32_t epoch, int tid, int* s_err) {
+// (sys_fence: the CTA's earlier stores must be visible to other GPUs before anything CTA 0 publishes afterwards; one
+// cumulative fence by thread 0 after the CTA barrier covers the whole CTA)
+__device__ __forceinline__ void gather_to_cta0(uint32_t* arrive, uint32_t epoch, int tid, int* s_err, bool sys_fence = false) {
     __syncthreads();
-    if (tid == 0) asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(arrive + blockIdx.x), "r"(epoch) : "memory");
+    if (tid == 0) {
+        if (sys_fence) __threadfence_system();
+        asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(arrive + blockIdx.x), "r"(epoch) : "memory");
+    }
     if (blockIdx.x == 0) {
         if (tid < int(gridDim.x)) {
             const long long t0 = clock64();
@@ -319,6 +324,7 @@ nvls_allreduce_adam_kernel(const NvlsArgs pa, float* __restrict__ params, float*
     }
     pdl_wait();
     pdl_trigger();
+    PEER_STAMP(0);
     const uint32_t epoch = ctrl[0] + 1;
     if (tid == 0) s_err = 0;
     __syncthreads();
@@ -331,6 +337,7 @@ nvls_allreduce_adam_kernel(const NvlsArgs pa, float* __restrict__ params, float*
     xgpu_wait(pa.blk_local + 0 * 8, R, epoch, tid, &s_err);
     if (s_err) { if (tid == 0) atomicExch(ctrl + 4, 1u); return; }
 
+    PEER_STAMP(1);
     // ---- 2. in-switch reduction of the owned slice ----
     double sa = 0.0, sc = 0.0;
 #pragma unroll
@@ -343,6 +350,7 @@ nvls_allreduce_adam_kernel(const NvlsArgs pa, float* __restrict__ params, float*
             if (i < na) sa += double(q); else sc += double(q);
         }
     }
+    PEER_STAMP(2);
     sa = block_sum(sa, s_scr);
     sc = block_sum(sc, s_scr);
     if (tid == 0) { partials[2 * blockIdx.x] = sa; partials[2 * blockIdx.x + 1] = sc; }
@@ -376,6 +384,7 @@ nvls_allreduce_adam_kernel(const NvlsArgs pa, float* __restrict__ params, float*
     }
     __syncthreads();
 
+    PEER_STAMP(3);
     // ---- 4. scalars, Adam on the owned slice, broadcast of the new parameters ----
     const int64_t t = *adam_step + 1;
     const float inv_world = float(hp[PPOAF_HP_INV_WORLD]);
@@ -418,11 +427,13 @@ nvls_allreduce_adam_kernel(const NvlsArgs pa, float* __restrict__ params, float*
         }
         m4[i] = make_float4(mm[0], mm[1], mm[2], mm[3]);
         v4[i] = make_float4(vv[0], vv[1], vv[2], vv[3]);
-        multimem_st_f4(pa.s_mc + 4 * i, make_float4(p[0], p[1], p[2], p[3]));
+        reinterpret_cast<float4*>(pa.s_local)[i] = make_float4(p[0], p[1], p[2], p[3]);
     }
-    __threadfence_system();                    // this thread's broadcast stores are ordered before the flags below
 
+    PEER_STAMP(4);
     // ---- 5. third barrier: every rank's slice has landed in every staging buffer ----
+    // the staging stores become visible GPU-wide through the release below; the peers read them from this GPU's L2, so
+    // the only system-scope ordering needed is CTA 0's cumulative release of the flag (a per-CTA fence.sys cost ~10 us)
     gather_to_cta0(arrive + gridDim.x, epoch, tid, &s_err);
     if (blockIdx.x == 0 && tid < R) {
         __threadfence_system();
@@ -430,7 +441,15 @@ nvls_allreduce_adam_kernel(const NvlsArgs pa, float* __restrict__ params, float*
     }
     xgpu_wait(pa.blk_local + 2 * 8, R, epoch, tid, &s_err);
     if (s_err) { if (tid == 0) atomicExch(ctrl + 4, 3u); return; }
-    for (int64_t i = gtid; i < nv; i += gstride) p4[i] = __ldcg(reinterpret_cast<const float4*>(pa.s_local) + i);
+    PEER_STAMP(5);
+    for (int64_t i = gtid; i < nv; i += gstride) {           // every slice straight from its owner's staging buffer
+        const int owner = int(i / slice);
+        float4 x;
+        asm volatile("ld.relaxed.sys.global.v4.f32 {%0,%1,%2,%3}, [%4];"
+                     : "=f"(x.x), "=f"(x.y), "=f"(x.z), "=f"(x.w) : "l"(reinterpret_cast<const float4*>(pa.s_peer[owner]) + i) : "memory");
+        p4[i] = x;
+    }
+    PEER_STAMP(6);
 
     // ---- the last CTA to finish advances the counters ----
     __syncthreads();
@@ -534,17 +553,17 @@ extern "C" size_t ppoaf_nvls_ctrl_bytes(void) {
 }
 extern "C" size_t ppoaf_nvls_flag_block_bytes(void) { return 256; }
 
-// g_mc / s_mc: multicast addresses of this parity's gradient buffer and of the parameter staging buffer;
-// s_local: this rank's staging buffer; flag_blocks[r]: rank r's zero-initialised flag block mapped on this device
+// g_mc: multicast address of this parity's gradient buffer; staging[r]: rank r's parameter staging buffer mapped on
+// this device; flag_blocks[r]: rank r's zero-initialised flag block mapped on this device
 // (ppoaf_nvls_flag_block_bytes() bytes, symmetric memory); ctrl: local zeroed scratch of ppoaf_nvls_ctrl_bytes().
-extern "C" int ppoaf_nvls_allreduce_adam(const float* g_mc, float* s_mc, const float* s_local, void* const* flag_blocks,
+extern "C" int ppoaf_nvls_allreduce_adam(const float* g_mc, void* const* staging, void* const* flag_blocks,
                                          int32_t n_ranks, int32_t my_rank, float* params, float* adam_m, float* adam_v,
                                          int64_t* adam_step, int32_t* mb_cursor, const double* hparams, int64_t n_actor,
                                          int64_t n_critic, void* ctrl, void* stream) {
     PPOAF_CHECK_ARG(n_ranks >= 2 && n_ranks <= kPeerMaxRanks && my_rank >= 0 && my_rank < n_ranks,
                     "ppoaf_nvls_allreduce_adam: 2..%d ranks", kPeerMaxRanks);
     PPOAF_CHECK_ARG(n_actor % 4 == 0 && n_critic % 4 == 0, "ppoaf_nvls_allreduce_adam: segments must be multiples of 4 floats");
-    PPOAF_CHECK_ARG(g_mc && s_mc && s_local, "ppoaf_nvls_allreduce_adam: null multicast pointers");
+    PPOAF_CHECK_ARG(g_mc && staging && flag_blocks, "ppoaf_nvls_allreduce_adam: null pointers");
     const int64_t n_total = n_actor + n_critic;
     const int64_t nv = n_total / 4;
     const int64_t slice = (nv + n_ranks - 1) / n_ranks;
@@ -554,8 +573,12 @@ extern "C" int ppoaf_nvls_allreduce_adam(const float* g_mc, float* s_mc, const f
     PPOAF_CHECK_ARG(slice <= int64_t(grid) * kPeerThreads * kPeerMaxVec,
                     "ppoaf_nvls_allreduce_adam: %lld parameters exceed the register-resident limit", (long long)n_total);
     NvlsArgs pa{};
-    pa.g_mc = g_mc; pa.s_mc = s_mc; pa.s_local = s_local;
-    for (int r = 0; r < n_ranks; ++r) pa.blk_peer[r] = static_cast<uint32_t*>(flag_blocks[r]);
+    pa.g_mc = g_mc;
+    pa.s_local = static_cast<float*>(staging[my_rank]);
+    for (int r = 0; r < n_ranks; ++r) {
+        pa.blk_peer[r] = static_cast<uint32_t*>(flag_blocks[r]);
+        pa.s_peer[r] = static_cast<const float*>(staging[r]);
+    }
     pa.blk_local = static_cast<uint32_t*>(flag_blocks[my_rank]);
     pa.n_ranks = n_ranks; pa.my_rank = my_rank;
     double* partials = static_cast<double*>(ctrl);

@@ -133,9 +133,8 @@ class NvlsGroup:
         self.grads = [self._buf[k * slot:k * slot + self.n_floats] for k in range(2)]
         self.mirror_delta = []
         self._g_mc = [mc + k * slot * 4 for k in range(2)]
-        self._s_mc = mc + 2 * slot * 4
-        self._s_local = base + 2 * slot * 4
         peers = [int(p) for p in self._hdl.buffer_ptrs]
+        self._staging = (C.c_void_p * self.world)(*[peers[r] + 2 * slot * 4 for r in range(self.world)])
         self._blocks = (C.c_void_p * self.world)(*[peers[r] + 3 * slot * 4 for r in range(self.world)])
         self._ctrl_bytes = lib.ppoaf_nvls_ctrl_bytes()
         self.ctrl = torch.zeros(self._ctrl_bytes, dtype=torch.uint8, device=self.device)
@@ -143,7 +142,7 @@ class NvlsGroup:
 
     def allreduce_adam(self, parity, nets, mb_cursor, hparams, stream_ptr):
         check(load().ppoaf_nvls_allreduce_adam(
-            C.c_void_p(self._g_mc[parity]), C.c_void_p(self._s_mc), C.c_void_p(self._s_local), self._blocks, self.world,
+            C.c_void_p(self._g_mc[parity]), self._staging, self._blocks, self.world,
             self.rank, C.c_void_p(nets.flat_params.data_ptr()), C.c_void_p(nets.adam_m.data_ptr()),
             C.c_void_p(nets.adam_v.data_ptr()), C.c_void_p(nets.adam_step.data_ptr()), C.c_void_p(mb_cursor.data_ptr()),
             C.c_void_p(hparams.data_ptr()), nets.n_actor, nets.n_critic, C.c_void_p(self.ctrl.data_ptr()), stream_ptr),
@@ -162,9 +161,12 @@ class NvlsGroup:
 
 
 def make_exchange_group(n_floats, device):
-    """NVLS (multicast) when the system offers it and PPOAF_NVLS != 0, else the push exchange over CUDA IPC."""
+    """The push exchange over CUDA IPC by default; PPOAF_NVLS=1 selects the NVSwitch-multicast two-shot exchange when
+    the system offers a multicast mapping.  Measured on 8 x B200 (C4, us per minibatch step, push / NVLS):
+    R=2 111 / 118, R=4 116 / 135, R=8 133 / 146 -- three cross-GPU barrier rounds cost more than the bytes they save at
+    1.84 MB of gradients, so NVLS stays opt-in until the parameter count makes the exchange bandwidth-bound."""
     import os
-    if os.environ.get("PPOAF_NVLS", "1") != "0" and NvlsGroup.available():
+    if os.environ.get("PPOAF_NVLS", "0") == "1" and NvlsGroup.available():
         ok = torch.zeros(1, dtype=torch.int32, device=device)
         grp = None
         try:
