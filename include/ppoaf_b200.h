@@ -225,6 +225,16 @@ int ppoaf_head_evaluate(int32_t head, const float* actor_out, int32_t pred_dim, 
                         float min_std, const void* actions, int32_t act_dim, int32_t n_rows,
                         float* log_prob_out, float* entropy_out, void* stream);
 
+/* "Next" row 1: rollout-time sampling, PPOPolicy.get_rollout_actions (policies/ppo_policy.py:729-794,
+ * networks/distributions.py:518-655, 199-249).  `noise` holds the draws of the HOST generator in the order the reference's
+ * CPU sampling consumes them -- N(0,1) [n_rows, act_dim] for the Gaussian head, Exp(1) [n_rows, pred_dim] for the
+ * Categorical head (aten multinomial's one-sample path) -- so the sampled actions are the reference's.  Outputs:
+ * raw_action / action fp32 [n_rows, act_dim] (Gaussian; action = tanh(raw) mapped to [dist_min, dist_max] when given) or
+ * int64 [n_rows, 1] (Categorical), log_prob fp32 [n_rows]. */
+int ppoaf_head_sample(int32_t head, const float* actor_out, int32_t pred_dim, const float* log_std, float min_std,
+                      const float* noise, const float* dist_min, const float* dist_max, int32_t act_dim,
+                      int32_t n_rows, void* raw_action_out, void* action_out, float* log_prob_out, void* stream);
+
 /* ------------------------------------------------------------------------------------------
  * P5  Gradient all-reduce over NVLink peer memory FUSED with clip + Adam (R > 1 on one node).
  * Replaces mpi_avg_gradients (utils/mpi_utils.py:89-111) + clip_grad_norm_ + Adam.step

@@ -82,6 +82,7 @@ _SIGNATURES = {
     "ppoaf_mlp_forward_workspace_bytes": (C.c_size_t, [C.POINTER(MlpDesc), C.c_int32]),
     "ppoaf_mlp_forward": (C.c_int, [C.POINTER(MlpDesc), _P, _P, _P, C.c_int32, C.c_int, _P, _P, C.c_size_t, _P]),
     "ppoaf_head_evaluate": (C.c_int, [C.c_int32, _P, C.c_int32, _P, C.c_float, _P, C.c_int32, C.c_int32, _P, _P, _P]),
+    "ppoaf_head_sample": (C.c_int, [C.c_int32, _P, C.c_int32, _P, C.c_float, _P, _P, _P, C.c_int32, C.c_int32, _P, _P, _P, _P]),
     "ppoaf_nvls_ctrl_bytes": (C.c_size_t, []),
     "ppoaf_nvls_flag_block_bytes": (C.c_size_t, []),
     "ppoaf_nvls_allreduce_adam": (C.c_int, [_P, C.POINTER(C.c_void_p), C.POINTER(C.c_void_p), C.c_int32, C.c_int32, _P, _P, _P,

@@ -635,6 +635,82 @@ __global__ void head_evaluate_kernel(int head, const float* __restrict__ actor_o
 
 }  // namespace ppoaf
 
+namespace ppoaf {
+
+// Rollout-time sampling (PPOPolicy.get_rollout_actions, policies/ppo_policy.py:729-794).  The random draws come from the
+// HOST generator in the order the reference's CPU sampling consumes them (`noise`), so the actions are the reference's
+// actions; everything else -- scaling by std, tanh squashing, range mapping, log-prob -- happens here.
+//   Gaussian:    noise = N(0,1) [n, act_dim];  raw = noise * std + mean  (torch.normal: mul_ then add_)
+//                action = tanh(raw), mapped to [min, max] when given (distributions.py:560-610); log-prob :518-558
+//   Categorical: noise = Exp(1) [n, pred];  sample = argmax(p / noise)  (aten multinomial, one draw); log-prob :223-249
+__global__ void head_sample_kernel(int head, const float* __restrict__ actor_out, int pred_dim,
+                                   const float* __restrict__ log_std, float min_std, const float* __restrict__ noise,
+                                   const float* __restrict__ dist_min, const float* __restrict__ dist_max, int act_dim,
+                                   int n_rows, void* __restrict__ raw_out, void* __restrict__ act_out,
+                                   float* __restrict__ lp_out) {
+    __shared__ float s_sd[kMaxAct];
+    const bool gaussian = head == PPOAF_HEAD_GAUSSIAN_TANH;
+    if (gaussian && threadIdx.x < act_dim) s_sd[threadIdx.x] = fmaxf(softplus_torch(log_std[threadIdx.x]), min_std);
+    __syncthreads();
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n_rows) return;
+    const float* pred = actor_out + int64_t(i) * pred_dim;
+    if (gaussian) {
+        const float* z = noise + int64_t(i) * act_dim;
+        float* raw = reinterpret_cast<float*>(raw_out) + int64_t(i) * act_dim;
+        float* act = reinterpret_cast<float*>(act_out) + int64_t(i) * act_dim;
+        float nsum = 0.f, slog = 0.f;
+        for (int d = 0; d < act_dim; ++d) {
+            const float mu = pred[d], sd = s_sd[d];
+            const float x = __fadd_rn(__fmul_rn(z[d], sd), mu);
+            const float th = tanhf(x);
+            float a = th;
+            if (dist_min && dist_max)
+                a = __fadd_rn(__fmul_rn(__fdiv_rn(__fadd_rn(th, 1.f), 2.f), __fsub_rn(dist_max[d], dist_min[d])), dist_min[d]);
+            raw[d] = x;
+            act[d] = a;
+            const float dz = x - mu;
+            nsum += fminf(fmaxf(-(dz * dz) / (2.f * (sd * sd)) - logf(sd) - kLogSqrt2Pi, -100.f), 100.f);
+            slog += logf(fmaxf(1.f - th * th, 1e-6f));
+        }
+        lp_out[i] = nsum - slog;
+    } else {
+        const float* q = noise + int64_t(i) * pred_dim;
+        float S = 0.f;
+        for (int c = 0; c < pred_dim; ++c) S += pred[c];
+        int best = 0;
+        float best_v = -INFINITY, best_p = 0.f;
+        for (int c = 0; c < pred_dim; ++c) {
+            const float pn = pred[c] / S;
+            const float v = pn / q[c];
+            if (v > best_v) { best_v = v; best = c; best_p = pn; }          // first maximum, like argmax
+        }
+        reinterpret_cast<int64_t*>(raw_out)[i] = best;
+        reinterpret_cast<int64_t*>(act_out)[i] = best;
+        lp_out[i] = logf(fminf(fmaxf(best_p, kCatEps), 1.f - kCatEps));
+    }
+}
+
+}  // namespace ppoaf
+
+extern "C" int ppoaf_head_sample(int32_t head, const float* actor_out, int32_t pred_dim, const float* log_std,
+                                 float min_std, const float* noise, const float* dist_min, const float* dist_max,
+                                 int32_t act_dim, int32_t n_rows, void* raw_action_out, void* action_out,
+                                 float* log_prob_out, void* stream) {
+    using namespace ppoaf;
+    PPOAF_CHECK_ARG(head == PPOAF_HEAD_GAUSSIAN_TANH || head == PPOAF_HEAD_CATEGORICAL, "ppoaf_head_sample: unknown head");
+    PPOAF_CHECK_ARG(act_dim >= 1 && act_dim <= kMaxAct && pred_dim >= 1 && pred_dim <= kMaxAct,
+                    "ppoaf_head_sample: widths must be in [1, %d]", kMaxAct);
+    PPOAF_CHECK_ARG(n_rows >= 0 && noise != nullptr, "ppoaf_head_sample: bad arguments");
+    PPOAF_CHECK_ARG((dist_min == nullptr) == (dist_max == nullptr), "ppoaf_head_sample: give both range bounds or neither");
+    if (n_rows == 0) return 0;
+    head_sample_kernel<<<(n_rows + 127) / 128, 128, 0, (cudaStream_t)stream>>>(
+        head, actor_out, pred_dim, log_std, min_std, noise, dist_min, dist_max, act_dim, n_rows, raw_action_out, action_out,
+        log_prob_out);
+    PPOAF_CHECK_LAUNCH("ppoaf_head_sample");
+    return 0;
+}
+
 extern "C" int ppoaf_head_evaluate(int32_t head, const float* actor_out, int32_t pred_dim, const float* log_std,
                                    float min_std, const void* actions, int32_t act_dim, int32_t n_rows,
                                    float* log_prob_out, float* entropy_out, void* stream) {

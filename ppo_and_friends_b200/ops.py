@@ -145,6 +145,24 @@ def head_evaluate(head, actor_out, log_std, actions, min_std=0.01, want_entropy=
     return lp, ent
 
 
+def head_sample(head, actor_out, log_std, noise, min_std=0.01, dist_min=None, dist_max=None, act_dim=1):
+    """(raw_action, action, log_prob) from the actor output and host-drawn noise (see ppoaf_head_sample)."""
+    n, pred = actor_out.shape
+    dev = actor_out.device
+    gaussian = head == _lib.HEAD_GAUSSIAN_TANH
+    if gaussian:
+        raw = torch.empty((n, act_dim), dtype=torch.float32, device=dev)
+        act = torch.empty((n, act_dim), dtype=torch.float32, device=dev)
+    else:
+        raw = torch.empty((n, 1), dtype=torch.int64, device=dev)
+        act = torch.empty((n, 1), dtype=torch.int64, device=dev)
+    lp = torch.empty(n, dtype=torch.float32, device=dev)
+    check(load().ppoaf_head_sample(int(head), ptr(actor_out), pred, ptr(log_std), float(min_std), ptr(noise), ptr(dist_min),
+                                   ptr(dist_max), int(act_dim), n, ptr(raw), ptr(act), ptr(lp), stream_ptr()),
+          "ppoaf_head_sample")
+    return raw, act, lp
+
+
 def clip_adam_step(params, grads, m, v, adam_step, hparams, n_actor, n_critic):
     lib = load()
     ws = _workspace("adam", 1 << 16, params.device)

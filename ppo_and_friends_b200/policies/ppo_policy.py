@@ -279,7 +279,55 @@ class PPOPolicy:
         lp, ent = ops.head_evaluate(self.head, pred, log_std, acts, self.min_std)
         return values, lp, ent
 
+    def get_rollout_actions(self, obs):
+        """
+        (raw_action, action, log_prob) for a batch of observations, with natural exploration
+        (reference policies/ppo_policy.py:729-794).  The actor forward, the std scaling, the tanh squashing / range
+        mapping and the log-prob run on the device; the random draws come from torch's global CPU generator in exactly
+        the order the reference's CPU sampling consumes them (Normal.sample -> normal_(0, 1) of shape [n, act_dim];
+        Categorical.sample -> exponential_(1) of shape [n, n_actions]), so a seeded run reproduces the reference's
+        actions.  Returns numpy raw_action / action and a CPU log_prob tensor, like the reference.
+        """
+        obs = np.asarray(obs) if not torch.is_tensor(obs) else obs
+        if len(obs.shape) < 2:
+            abort("ERROR: get_rollout_actions expects a batch of observations but "
+                  "instead received shape {}.".format(tuple(obs.shape)))
+        t_obs = torch.as_tensor(obs, dtype=torch.float32).to(self.device).reshape(obs.shape[0], -1).contiguous()
+        n = t_obs.shape[0]
+        discrete = self.action_dtype != "continuous"
+        action_pred = self.actor(t_obs, softmax_out=discrete)
+        if discrete:
+            noise = torch.empty(n, self.action_pred_size, dtype=torch.float32).exponential_(1)
+            log_std = dist_min = dist_max = None
+        else:
+            noise = torch.empty(n, self.action_dim, dtype=torch.float32).normal_(0, 1)
+            log_std = self.actor.state_dict()["distribution.log_std"]
+            rescale = bool((self.dist_min != -1.0).any() or (self.dist_max != 1.0).any())
+            dist_min = self._dist_dev("min") if rescale else None
+            dist_max = self._dist_dev("max") if rescale else None
+        raw, act, lp = ops.head_sample(self.head, action_pred, log_std, noise.to(self.device, non_blocking=True),
+                                       self.min_std, dist_min, dist_max, act_dim=1 if discrete else self.action_dim)
+        # the reference aborts on NaN observations / predictions (:758-775); one check of the results covers both
+        bad = torch.isnan(t_obs).any() | torch.isnan(action_pred).any()
+        raw_h, act_h, lp_h, bad_h = raw.cpu(), act.cpu(), lp.cpu(), bool(bad.item())
+        if bad_h:
+            abort("ERROR: get_rollout_actions received observations or produced action predictions "
+                  "containing nan values!")
+        if discrete:
+            lp_h = lp_h.unsqueeze(-1)
+        return raw_h.numpy(), act_h.numpy(), lp_h
+
+    def _dist_dev(self, which):
+        """The Gaussian head's output range as device tensors (built once)."""
+        cache = self.__dict__.setdefault("_dist_dev_cache", {})
+        if which not in cache:
+            src = self.dist_min if which == "min" else self.dist_max
+            full = np.broadcast_to(src, (self.action_dim,)).astype(np.float32)
+            cache[which] = torch.as_tensor(np.ascontiguousarray(full)).to(self.device)
+        return cache[which]
+
     def get_critic_values(self, obs):
+        """Values of a batch of critic observations (reference policies/ppo_policy.py:1057-1071)."""
         return self.critic(obs)
 
     def update_weights(self, actor_loss, critic_loss):

@@ -328,7 +328,53 @@ def gen_updates():
         print(name, "N =", len(seg["advantages"]), {k: out[k] for k in out if k.endswith("status")})
 
 
+def gen_rollout_actions():
+    """Rollout-time inference: PPOPolicy.get_rollout_actions / get_critic_values of the unmodified
+    reference (policies/ppo_policy.py:729-794, 1057-1071) on seeded observations, with the global CPU generator seeded
+    right before the call (the sampling protocol the device path has to reproduce)."""
+    cases = {
+        "act_gauss": dict(ro=dict(seed=41, T=4, E=8, obs_dim=11, act_dim=3, obs_scale=False),
+                          net=dict(act="tanh", actor_hidden=32, critic_hidden=24)),
+        "act_gauss_range": dict(ro=dict(seed=42, T=4, E=5, obs_dim=6, act_dim=2, obs_scale=False),      # < 16 samples
+                                net=dict(act="leaky_relu", actor_hidden=16, critic_hidden=16, dist_range=0.4)),
+        "act_cat": dict(ro=dict(seed=43, T=4, E=16, obs_dim=7, n_discrete=5, obs_scale=False),
+                        net=dict(act="relu", actor_hidden=32, critic_hidden=32, depth=2)),
+    }
+    for name, c in cases.items():
+        ro = make_rollout(**c["ro"])
+        torch.manual_seed(1000 + c["ro"]["seed"])
+        pol = build_policy(ro, **c["net"])
+        out = {}
+        out.update(snapshot_net("init/actor", pol.actor, pol.actor_optim))
+        out.update(snapshot_net("init/critic", pol.critic, pol.critic_optim))
+        a = ro.agents[0]
+        for step in range(2):                       # two consecutive calls: the generator state carries over
+            obs = ro.obs[a][step].astype(np.float32)
+            if step == 0:
+                torch.manual_seed(5000 + c["ro"]["seed"])
+            raw, act, lp = pol.get_rollout_actions(obs)
+            with torch.no_grad():
+                val = pol.get_critic_values(torch.tensor(ro.critic_obs[a][step].astype(np.float32)))
+            out[f"s{step}/obs"] = obs
+            out[f"s{step}/critic_obs"] = ro.critic_obs[a][step].astype(np.float32)
+            out[f"s{step}/raw_action"] = np.asarray(raw).copy()
+            out[f"s{step}/action"] = np.asarray(act).copy()
+            out[f"s{step}/log_prob"] = lp.numpy().copy()
+            out[f"s{step}/value"] = val.numpy().copy()
+        hp = dict(sample_seed=5000 + c["ro"]["seed"], activation=np.array(c["net"]["act"]),
+                  dist_range=c["net"].get("dist_range", 1.0), actor_hidden=c["net"]["actor_hidden"],
+                  critic_hidden=c["net"]["critic_hidden"], depth=c["net"].get("depth", 3),
+                  n_discrete=ro.n_discrete, act_dim=ro.act_dim, obs_dim=ro.obs_dim, E=ro.E)
+        np.savez_compressed(os.path.join(HERE, name + ".npz"), **out, **{"hp_" + k: v for k, v in hp.items()})
+        print(name, {k: out[k].shape for k in out if k.startswith("s0/")})
+
+
 if __name__ == "__main__":
-    gen_segments()
-    gen_stats()
-    gen_updates()
+    import sys
+    if len(sys.argv) > 1 and sys.argv[1] == "actions":       # only the rollout-action fixtures (added later)
+        gen_rollout_actions()
+    else:
+        gen_segments()
+        gen_stats()
+        gen_updates()
+        gen_rollout_actions()

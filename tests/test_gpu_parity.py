@@ -414,6 +414,38 @@ def test_two_rank_update_matches_multirank_oracle(discrete, peer):
     assert res.returncode == 0 and "MULTI_GPU_CHECK PASS" in res.stdout, res.stdout[-3000:] + res.stderr[-3000:]
 
 
+# ----------------------------------------------------------------------------------------- §8f row 1: rollout-time inference
+@pytest.mark.parametrize("name", ["act_gauss", "act_gauss_range", "act_cat"])
+def test_rollout_actions_match_reference(name):
+    """PPOPolicy.get_rollout_actions / get_critic_values against the unmodified reference's outputs
+    (tests/golden/act_*.npz): same seed -> same sampled actions (integer actions bit-exact), log-probs and values
+    within 1e-5."""
+    from ppo_and_friends_b200.synthetic import make_rollout
+    g = load_golden(name)
+    n_disc = int(g["hp_n_discrete"])
+    ro = make_rollout(seed=1, T=2, E=int(g["hp_E"]), obs_dim=int(g["hp_obs_dim"]), act_dim=int(g["hp_act_dim"]),
+                      n_discrete=n_disc, obs_scale=False)
+    pol = make_policy(ro, act=str(g["hp_activation"]), actor_hidden=int(g["hp_actor_hidden"]),
+                      critic_hidden=int(g["hp_critic_hidden"]), depth=int(g["hp_depth"]),
+                      dist_range=float(g["hp_dist_range"]))
+    pol.actor.load_state_dict({k[len("init/actor/param/"):]: g[k] for k in g if k.startswith("init/actor/param/")})
+    pol.critic.load_state_dict({k[len("init/critic/param/"):]: g[k] for k in g if k.startswith("init/critic/param/")})
+    torch.manual_seed(int(g["hp_sample_seed"]))
+    for step in range(2):
+        raw, act, lp = pol.get_rollout_actions(g[f"s{step}/obs"])
+        assert raw.shape == g[f"s{step}/raw_action"].shape and act.shape == g[f"s{step}/action"].shape
+        assert tuple(lp.shape) == g[f"s{step}/log_prob"].shape
+        if n_disc:
+            assert raw.dtype == np.int64 and np.array_equal(raw, g[f"s{step}/raw_action"])
+            assert np.array_equal(act, g[f"s{step}/action"])
+        else:
+            np.testing.assert_allclose(raw, g[f"s{step}/raw_action"], rtol=1e-5, atol=1e-6)
+            np.testing.assert_allclose(act, g[f"s{step}/action"], rtol=1e-5, atol=1e-6)
+        np.testing.assert_allclose(lp.numpy(), g[f"s{step}/log_prob"], rtol=1e-5, atol=1e-5)
+        val = pol.get_critic_values(g[f"s{step}/critic_obs"])
+        np.testing.assert_allclose(val.cpu().numpy(), g[f"s{step}/value"], rtol=1e-5, atol=1e-6)
+
+
 # ----------------------------------------------------------------------------------------- A7 / P6 / P8
 def test_dataset_getitem_and_len_match_reference_rows():
     """PPODataset.__len__/__getitem__ (utils/episode_info.py:916-952): the 13-tuple of row idx."""
