@@ -175,7 +175,57 @@ class PolicyNetworks:
 
 
 class _AdamView:
-    """Just enough of torch.optim.Adam's surface for the trainer (`param_groups[i]['lr']`)."""
+    """
+    torch.optim.Adam's surface as the trainer and the checkpoints use it (`param_groups[i]['lr']`, `state_dict()`,
+    `load_state_dict()`), over the flat device buffers of one network.  The state dict has torch's layout
+    (`state[i] = {step, exp_avg, exp_avg_sq}` in `named_parameters()` order, one param group), so files written by the
+    reference's `torch.save(self.actor_optim.state_dict(), ...)` (policies/ppo_policy.py:1228-1247) load here and the
+    files written here load into a real `torch.optim.Adam`.
+    """
 
-    def __init__(self, lr):
+    def __init__(self, lr, net=None):
+        self.net = net
         self.param_groups = [dict(lr=lr, betas=(0.9, 0.999), eps=1e-5)]
+
+    def state_dict(self):
+        m, v = self.net.adam_dicts()
+        step = float(self.net.owner.adam_step.item())
+        state = {}
+        if step > 0:                                   # torch creates the per-parameter state at the first step
+            for i, k in enumerate(m):
+                state[i] = dict(step=torch.tensor(step, dtype=torch.float32), exp_avg=m[k].detach().cpu().clone(),
+                                exp_avg_sq=v[k].detach().cpu().clone())
+        g = self.param_groups[0]
+        group = dict(lr=g["lr"], betas=tuple(g["betas"]), eps=g["eps"], weight_decay=0, amsgrad=False, maximize=False,
+                     foreach=None, capturable=False, differentiable=False, fused=None, decoupled_weight_decay=False,
+                     params=list(range(len(m))))
+        return dict(state=state, param_groups=[group])
+
+    def load_state_dict(self, sd):
+        m, v = self.net.adam_dicts()
+        keys = list(m.keys())
+        state = sd.get("state", {})
+        steps = set()
+        with torch.no_grad():
+            for i, k in enumerate(keys):
+                st = state.get(i, state.get(str(i)))
+                if st is None:
+                    m[k].zero_(); v[k].zero_()
+                    continue
+                m[k].copy_(torch.as_tensor(st["exp_avg"]).to(m[k].device, torch.float32).reshape(m[k].shape))
+                v[k].copy_(torch.as_tensor(st["exp_avg_sq"]).to(v[k].device, torch.float32).reshape(v[k].shape))
+                steps.add(int(round(float(st["step"]))))
+        if len(steps) > 1:
+            raise ValueError(f"{self.net.name}: parameters with different Adam step counts {sorted(steps)} cannot be "
+                             "represented (the fused optimizer keeps one step counter)")
+        step = steps.pop() if steps else 0
+        owner = self.net.owner
+        if getattr(owner, "_loaded_adam_step", None) not in (None, step):
+            raise ValueError("actor and critic optimizers were saved at different step counts "
+                             f"({owner._loaded_adam_step} vs {step}); the fused optimizer keeps one step counter")
+        owner._loaded_adam_step = step
+        owner.adam_step.fill_(step)
+        groups = sd.get("param_groups") or [{}]
+        for key in ("lr", "betas", "eps"):
+            if key in groups[0]:
+                self.param_groups[0][key] = groups[0][key]

@@ -16,6 +16,8 @@ no counterpart because the losses never exist as tensors — the fused step in p
 (`ppo_batch_train`) replaces `PPO._ppo_batch_train` + `evaluate` + `update_weights` as one unit.
 Out of scope (raise): LSTM networks, ICM, MAT, Bernoulli/MultiCategorical/Mixed action heads.
 """
+import os
+
 import numpy as np
 import torch
 
@@ -23,7 +25,7 @@ from .. import _lib, ops
 from ..networks.feed_forward import PolicyNetworks, _AdamView, hidden_sizes
 from ..utils.episode_info import PPODataset, RolloutRing
 from ..utils.misc import update_optimizer_lr
-from ..utils.mpi_utils import abort, barrier, broadcast_model_parameters, rank_print
+from ..utils.mpi_utils import abort, barrier, broadcast_model_parameters, get_rank, rank_print
 
 
 class CallableValue:
@@ -142,8 +144,8 @@ class PPOPolicy:
         if self.have_bootstrap_clip:
             self.bootstrap_clip[0].finalize(status_dict)
             self.bootstrap_clip[1].finalize(status_dict)
-        self.actor_optim = _AdamView(self.lr())
-        self.critic_optim = _AdamView(self.lr())
+        self.actor_optim = _AdamView(self.lr(), self.actor)
+        self.critic_optim = _AdamView(self.lr(), self.critic)
         self.icm_optim = None
 
     def _initialize_networks(self):
@@ -335,6 +337,54 @@ class PPOPolicy:
             "PPOPolicy.update_weights(actor_loss, critic_loss) has no counterpart on the B200 path: losses are "
             "never materialised as autograd tensors. Use ppo_and_friends_b200.ppo.ppo_batch_train, which replaces "
             "PPO._ppo_batch_train + evaluate + update_weights as one fused step.")
+
+    # -- checkpoints (reference policies/ppo_policy.py:1152-1300): same directory layout and file formats ----------
+    def save(self, save_path, tag="latest"):
+        policy_save_path = os.path.join(save_path, "{}-policy".format(self.name), str(tag))
+        if get_rank() == 0 and not os.path.exists(policy_save_path):
+            os.makedirs(policy_save_path)
+        barrier()
+        self._save_policies(policy_save_path)
+        self._save_optimizers(policy_save_path)
+
+    def load(self, load_path, tag="latest"):
+        policy_load_path = os.path.join(load_path, "{}-policy".format(self.name), str(tag))
+        self._load_policies(policy_load_path)
+        self._load_optimizers(policy_load_path)
+
+    def _save_policies(self, save_path):
+        self.actor.save(save_path, get_rank())
+        self.critic.save(save_path, get_rank())
+
+    def _load_policies(self, load_path):
+        self.actor.load(load_path, get_rank())
+        self.critic.load(load_path, get_rank())
+
+    def _save_optimizers(self, save_path):
+        if self.test_mode:
+            return
+        torch.save(self.actor_optim.state_dict(), os.path.join(save_path, f"actor_optim_{get_rank()}"))
+        torch.save(self.critic_optim.state_dict(), os.path.join(save_path, f"critic_optim_{get_rank()}"))
+
+    def _load_optimizers(self, load_path):
+        if self.test_mode:
+            return
+        try:
+            files = []
+            for which in ("actor", "critic"):
+                f = os.path.join(load_path, f"{which}_optim_{get_rank()}")
+                if not os.path.exists(f):
+                    f = os.path.join(load_path, f"{which}_optim_0")
+                files.append(f)
+            self.nets._loaded_adam_step = None
+            self.actor_optim.load_state_dict(torch.load(files[0], weights_only=False))
+            self.critic_optim.load_state_dict(torch.load(files[1], weights_only=False))
+        except FileNotFoundError:
+            rank_print("WARNING: unable to find saved optimizers to load. Skipping...")
+
+    def direct_load(self, policy_load_path):
+        self.actor.load(policy_load_path, get_rank())
+        self.critic.load(policy_load_path, get_rank())
 
     def update_learning_rate(self):
         if self.frozen:

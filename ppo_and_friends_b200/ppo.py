@@ -83,6 +83,7 @@ class UpdateEngine:
         self.workspace = torch.zeros(ws_bytes + 256, dtype=torch.uint8, device=dev)
         self.null_state = torch.tensor([0.0, 1.0, 1e-4], dtype=torch.float64, device=dev)
         self._graphs = {}
+        self._spec_perm = None          # (n, rng state before, rng state after, permutation) drawn ahead of time
         self._graph_key = None
         self._perm_dev = None
         self.launches_per_step = None
@@ -191,13 +192,34 @@ class UpdateEngine:
             mpi_utils.mpi_avg_gradients(self.policy.nets.flat_grads)
             g[1].replay()
 
+    # -- the next epoch's permutation, drawn while the GPU is busy --------------------------------------------
+    # The draw must consume torch's global CPU generator exactly where the reference's DataLoader would: at the start of
+    # the next epoch, and only if that epoch happens (KL early stop, last epoch).  So the generator is rewound after the
+    # speculative draw, and the result is used only if the generator is found in exactly that state when the next epoch
+    # starts; the generator is then moved to where the draw had left it.
+    def _speculate_next_permutation(self, n):
+        before = torch.get_rng_state()
+        perm = draw_minibatch_permutation(n)
+        after = torch.get_rng_state()
+        torch.set_rng_state(before)
+        self._spec_perm = (n, before, after, perm)
+
+    def _take_speculated_permutation(self, n):
+        spec, self._spec_perm = self._spec_perm, None
+        if spec is None or spec[0] != n or not torch.equal(torch.get_rng_state(), spec[1]):
+            return None
+        torch.set_rng_state(spec[2])
+        return spec[3]
+
     # -- one epoch = PPO._ppo_batch_train -------------------------------------------------------------------
     def run_epoch(self, ds):
         n = len(ds)
         n_mb = self._ensure_epoch_buffers(n)
         lib = load()
         self.refresh_hparams()
-        perm = draw_minibatch_permutation(n)
+        perm = self._take_speculated_permutation(n)
+        if perm is None:
+            perm = draw_minibatch_permutation(n)
         self._perm_host.copy_(perm)
         self._perm_dev.copy_(self._perm_host, non_blocking=True)
         check(lib.ppoaf_epoch_prepare(ptr(self._perm_dev), ptr(ds.advantages), ptr(ds.rewards_to_go), n, self.batch_size,
@@ -214,6 +236,7 @@ class UpdateEngine:
             rows = min(self.batch_size, n - k * self.batch_size)
             self._launch_step(ds, rows)
         self.epoch_stats_host.copy_(self.epoch_stats, non_blocking=True)
+        self._speculate_next_permutation(n)                             # host work while the GPU runs the epoch
         torch.cuda.current_stream(self.device).synchronize()            # the one host sync of the epoch
         return self.epoch_stats_host.clone()
 

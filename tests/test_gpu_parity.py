@@ -504,3 +504,69 @@ def test_epoch_loop_kl_early_stop_and_lr_schedule():
     assert train_policies(state) == {"pol": 1}
     pol.target_kl = 1e9
     assert train_policies(state) == {"pol": 5}
+
+
+# ----------------------------------------------------------------------------------------- §8f row 3: checkpoints
+def _golden_adam_state(g, prefix, keys):
+    """torch.optim.Adam.state_dict() of the reference at `prefix` (the format policies/ppo_policy.py:1228-1247 saves)."""
+    state = {i: dict(step=torch.tensor(float(g[f"{prefix}/step/{k}"])), exp_avg=torch.tensor(g[f"{prefix}/exp_avg/{k}"]),
+                     exp_avg_sq=torch.tensor(g[f"{prefix}/exp_avg_sq/{k}"])) for i, k in enumerate(keys)}
+    return dict(state=state, param_groups=[dict(lr=float(g["hp_lr"]), betas=(0.9, 0.999), eps=1e-5, params=list(range(len(keys))))])
+
+
+def test_checkpoint_resume_from_reference_state_matches_reference_epoch(tmp_path):
+    """Write the reference's epoch-0 state (networks, Adam moments and step counts, value normaliser, dataset values)
+    in the reference's checkpoint formats, load it through PPOPolicy.load / RunningStatNormalizer.load_info, run
+    epoch 1 on the device and compare with the reference's epoch 1.  Then save and check that the optimizer file loads
+    into a real torch.optim.Adam."""
+    import pickle
+    name = "upd_gauss"
+    g = load_golden(name)
+    ro, pol = policy_from_update_golden(g)
+    ds = run_device_rollout(pol, ro)
+    # --- a checkpoint directory as the reference would have written it after epoch 0 ---
+    ckpt = tmp_path / "pol-policy" / "latest"
+    ckpt.mkdir(parents=True)
+    for net in ("actor", "critic"):
+        keys = [k[len(f"ep0/{net}/param/"):] for k in g if k.startswith(f"ep0/{net}/param/")]
+        torch.save({k: torch.tensor(g[f"ep0/{net}/param/{k}"]) for k in keys}, ckpt / f"{net}_0.model")
+        torch.save(_golden_adam_state(g, f"ep0/{net}", keys), ckpt / f"{net}_optim_0")
+    pol.load(str(tmp_path))
+    assert int(pol.nets.adam_step.item()) == int(g["ep0/actor/step/" + keys[0]])
+    from ppo_and_friends_b200.ppo import PPOUpdateState, _Loader, draw_minibatch_permutation, ppo_batch_train
+    state = PPOUpdateState({"pol": pol}, batch_size=int(g["hp_B"]), epochs_per_iter=1, device="cuda",
+                           normalize_adv=bool(g["hp_normalize_adv"]), normalize_values=bool(g["hp_normalize_values"]))
+    mean, var, count = g["ep0/vn"]
+    state.value_normalizers["pol"].running_stats.load_reference(mean, var, count)
+    ds.values.copy_(torch.tensor(g["ep0/dataset_values"]).to(ds.values.device))
+    torch.manual_seed(int(g["hp_perm_seed"]))
+    draw_minibatch_permutation(len(ds))                     # epoch 0's draws: the generator is where epoch 1 found it
+    ppo_batch_train(state, _Loader(ds, int(g["hp_B"])), "pol")
+    sd = state.status_dict["pol"]
+    ref = g["ep1/status"]
+    for got, want in zip((sd["actor loss"], sd["critic loss"], sd["kl avg"], sd["weighted entropy"]), ref):
+        assert abs(got - want) <= 1e-4 * max(abs(want), 1e-3)
+    for net, obj in (("actor", pol.actor), ("critic", pol.critic)):
+        for k, v in obj.state_dict().items():
+            np.testing.assert_allclose(v.cpu().numpy(), g[f"ep1/{net}/param/{k}"], rtol=1e-4, atol=1e-6, err_msg=k)
+    # --- save, and load the optimizer file into a real torch Adam ---
+    out = tmp_path / "out"
+    pol.save(str(out))
+    for net, obj in (("actor", pol.actor), ("critic", pol.critic)):
+        params = [torch.nn.Parameter(v.detach().cpu().clone()) for v in obj.state_dict().values()]
+        opt = torch.optim.Adam(params, lr=1e-3, eps=1e-5)
+        opt.load_state_dict(torch.load(out / "pol-policy" / "latest" / f"{net}_optim_0", weights_only=False))
+        st = opt.state_dict()["state"]
+        for i, k in enumerate(obj.state_dict()):
+            np.testing.assert_allclose(st[i]["exp_avg"].numpy(), g[f"ep1/{net}/exp_avg/{k}"], rtol=1e-4, atol=1e-7)
+            assert float(st[i]["step"]) == float(g[f"ep1/{net}/step/{k}"])
+        sd2 = torch.load(out / "pol-policy" / "latest" / f"{net}_0.model")
+        assert list(sd2.keys()) == list(obj.state_dict().keys())
+    # the value normaliser pickles with host arrays and round-trips
+    vn = state.value_normalizers["pol"]
+    vn.save_info(str(out))
+    before = (vn.running_stats.mean.copy(), vn.running_stats.variance.copy(), vn.running_stats.count)
+    vn.running_stats.load_reference(0.0, 1.0, 1e-4)
+    vn.load_info(str(out))
+    assert np.allclose(vn.running_stats.mean, before[0]) and np.allclose(vn.running_stats.variance, before[1])
+    assert vn.running_stats.count == before[2]

@@ -207,3 +207,37 @@ def test_value_stat_merge_order_matches_allgather_semantics():
     mine = OracleRunningMeanStd()
     mine.integrate(mean, M2 / n, n)
     assert abs(mine.mean - ref.mean) < 1e-6 and abs(mine.variance - ref.variance) < 1e-5 * ref.variance
+
+
+def test_speculated_permutation_keeps_the_generator_protocol():
+    """The permutation of the next epoch is drawn ahead of time (while the GPU runs the current epoch); it may only be
+    used if nothing touched torch's global generator in between, and the generator must end up exactly where the
+    reference's DataLoader would have left it."""
+    import types
+    from ppo_and_friends_b200.ppo import UpdateEngine, draw_minibatch_permutation
+    eng = types.SimpleNamespace(_spec_perm=None)
+    n = 257
+    # reference sequence: two epochs drawn back to back, then one more global draw
+    torch.manual_seed(99)
+    ref = [draw_minibatch_permutation(n), draw_minibatch_permutation(n)]
+    ref_next = torch.empty((), dtype=torch.int64).random_().item()
+    # speculated sequence
+    torch.manual_seed(99)
+    p0 = draw_minibatch_permutation(n)
+    UpdateEngine._speculate_next_permutation(eng, n)
+    p1 = UpdateEngine._take_speculated_permutation(eng, n)
+    assert p1 is not None and torch.equal(p0, ref[0]) and torch.equal(p1, ref[1])
+    assert torch.empty((), dtype=torch.int64).random_().item() == ref_next
+    # the epoch loop stops early: the speculation must leave no trace in the generator
+    torch.manual_seed(99)
+    draw_minibatch_permutation(n)
+    UpdateEngine._speculate_next_permutation(eng, n)
+    other = torch.empty((), dtype=torch.int64).random_().item()          # e.g. rollout sampling
+    torch.manual_seed(99)
+    draw_minibatch_permutation(n)
+    assert other == torch.empty((), dtype=torch.int64).random_().item()
+    # ... and a speculation made before that foreign draw must be discarded
+    assert UpdateEngine._take_speculated_permutation(eng, n) is None
+    # a different dataset size also discards it
+    UpdateEngine._speculate_next_permutation(eng, n)
+    assert UpdateEngine._take_speculated_permutation(eng, n + 1) is None
