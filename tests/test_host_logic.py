@@ -241,3 +241,50 @@ def test_speculated_permutation_keeps_the_generator_protocol():
     # a different dataset size also discards it
     UpdateEngine._speculate_next_permutation(eng, n)
     assert UpdateEngine._take_speculated_permutation(eng, n + 1) is None
+
+
+def test_adam_view_state_dict_is_torch_adam_compatible():
+    """The optimizer stand-in of the fused update reads and writes torch.optim.Adam state dicts (the format of the
+    reference's `actor_optim_<rank>` checkpoint files, policies/ppo_policy.py:1228-1247).  Host-only: buffers on CPU."""
+    from ppo_and_friends_b200.networks.feed_forward import PolicyNetworks, _AdamView
+    torch.manual_seed(3)
+    nets = PolicyNetworks("cpu", [5, 8, 8, 3], [5, 6, 1], torch.nn.Tanh(), torch.nn.Tanh(), gaussian=True, act_dim=3)
+    nets.adam_m.copy_(torch.randn_like(nets.adam_m))
+    nets.adam_v.copy_(torch.rand_like(nets.adam_v))
+    nets.adam_step.fill_(7)
+    views = {"actor": _AdamView(1e-3, nets.actor), "critic": _AdamView(1e-3, nets.critic)}
+    saved = {}
+    for name, view in views.items():
+        net = getattr(nets, name)
+        sd = view.state_dict()
+        saved[name] = sd
+        params = [torch.nn.Parameter(v.detach().clone()) for v in net.state_dict().values()]
+        opt = torch.optim.Adam(params, lr=5e-4, eps=1e-5)
+        opt.load_state_dict(sd)                                   # a real torch Adam accepts the file
+        st = opt.state_dict()["state"]
+        m, v = net.adam_dicts()
+        assert len(st) == len(m)
+        for i, k in enumerate(m):
+            assert torch.equal(st[i]["exp_avg"], m[k]) and torch.equal(st[i]["exp_avg_sq"], v[k])
+            assert float(st[i]["step"]) == 7.0
+        assert opt.state_dict()["param_groups"][0]["lr"] == 1e-3
+    # and back: wipe the buffers, load what torch wrote
+    nets2 = PolicyNetworks("cpu", [5, 8, 8, 3], [5, 6, 1], torch.nn.Tanh(), torch.nn.Tanh(), gaussian=True, act_dim=3)
+    for name in ("actor", "critic"):
+        _AdamView(1e-3, getattr(nets2, name)).load_state_dict(saved[name])
+    for name in ("actor", "critic"):                             # (the flat buffers also hold alignment padding)
+        (m1, v1), (m2, v2) = getattr(nets, name).adam_dicts(), getattr(nets2, name).adam_dicts()
+        for k in m1:
+            assert torch.equal(m1[k], m2[k]) and torch.equal(v1[k], v2[k])
+    assert int(nets2.adam_step.item()) == 7
+    # different step counts for actor and critic cannot be represented by the single fused counter
+    bad = {k: dict(v) for k, v in saved["critic"]["state"].items()}
+    for v in bad.values():
+        v["step"] = torch.tensor(9.0)
+    nets3 = PolicyNetworks("cpu", [5, 8, 8, 3], [5, 6, 1], torch.nn.Tanh(), torch.nn.Tanh(), gaussian=True, act_dim=3)
+    _AdamView(1e-3, nets3.actor).load_state_dict(saved["actor"])
+    with pytest.raises(ValueError):
+        _AdamView(1e-3, nets3.critic).load_state_dict(dict(state=bad, param_groups=saved["critic"]["param_groups"]))
+    # a fresh optimizer (no step yet) has an empty state, like torch's
+    nets4 = PolicyNetworks("cpu", [5, 8, 8, 3], [5, 6, 1], torch.nn.Tanh(), torch.nn.Tanh(), gaussian=True, act_dim=3)
+    assert _AdamView(1e-3, nets4.actor).state_dict()["state"] == {}
