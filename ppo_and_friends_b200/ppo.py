@@ -192,6 +192,33 @@ class UpdateEngine:
             mpi_utils.mpi_avg_gradients(self.policy.nets.flat_grads)
             g[1].replay()
 
+    def _launch_full_minibatches(self, ds, n_full):
+        """All full minibatches of an epoch as ONE captured graph: every step is the same chain of launches driven by
+        the device-side cursor, so the epoch is n_full copies of it.  Compared with n_full replays of a one-step graph
+        this removes the graph-launch gap between steps and lets the programmatic dependencies span step boundaries
+        (the first forward GEMM of step k+1 sets up while the optimizer of step k drains)."""
+        start = self.step_parity if self.peer is not None else 0
+        key = ("epoch", n_full, start, ds.observations.data_ptr(), ds.critic_observations.data_ptr(),
+               ds.values.data_ptr(), ds.advantages.data_ptr())
+        g = self._graphs.get(key)
+        if g is None:
+            if len(self._graphs) > 16:
+                self._graphs.clear()
+
+            def body():
+                par = start
+                for _ in range(n_full):
+                    self._step_eager(self._bufs(ds, self.batch_size, par), par)
+                    if self.peer is not None:
+                        par ^= 1
+            g = (self._capture(body), None, None)
+            self._graphs[key] = g
+        g[0].replay()
+        if self.peer is not None:
+            last = start ^ ((n_full - 1) & 1)
+            self.step_parity = last ^ 1
+            self.policy.nets.flat_grads = self.peer.grads[last]
+
     # -- the next epoch's permutation, drawn while the GPU is busy --------------------------------------------
     # The draw must consume torch's global CPU generator exactly where the reference's DataLoader would: at the start of
     # the next epoch, and only if that epoch happens (KL early stop, last epoch).  So the generator is rewound after the
@@ -232,9 +259,16 @@ class UpdateEngine:
                                                  ptr(self._mb_val_stats), stream_ptr()), "ppoaf_value_stats_sequence")
         self.epoch_stats.zero_()
         self.mb_cursor.zero_()
-        for k in range(n_mb):
-            rows = min(self.batch_size, n - k * self.batch_size)
-            self._launch_step(ds, rows)
+        n_full = n // self.batch_size
+        if (self.use_graphs and n_full >= 2 and os.environ.get("PPOAF_EPOCH_GRAPH", "1") != "0"
+                and (mpi_utils.get_num_procs() == 1 or self.peer is not None)):
+            self._launch_full_minibatches(ds, n_full)          # ONE graph for all full minibatches of the epoch
+            if n - n_full * self.batch_size > 0:
+                self._launch_step(ds, n - n_full * self.batch_size)
+        else:
+            for k in range(n_mb):
+                rows = min(self.batch_size, n - k * self.batch_size)
+                self._launch_step(ds, rows)
         self.epoch_stats_host.copy_(self.epoch_stats, non_blocking=True)
         self._speculate_next_permutation(n)                             # host work while the GPU runs the epoch
         torch.cuda.current_stream(self.device).synchronize()            # the one host sync of the epoch
