@@ -191,7 +191,10 @@ class HotPath:
         """Kernels of libppoaf_b200.so launched per step (torch's own fills / copies are not counted)."""
         world = torch.distributed.get_world_size() if torch.distributed.is_initialized() else 1
         layers = 4                                         # Linear layers per net (hidden_depth 3 + output)
-        per_mb = layers + 1 + layers + 1 + (1 if world > 1 else 0)   # grouped fwd, loss, grouped bwd, [norm,] adam
+        # grouped fwd (heads are fused into the loss kernel), loss + heads, grouped bwd, optimizer (R > 1: the fused
+        # exchange + clip + Adam kernel; only the NCCL fallback adds a norm pass)
+        nccl = world > 1 and os.environ.get("PPOAF_PEER", "1") == "0"
+        per_mb = (layers - 1) + 1 + (layers - 1) + 1 + (1 if nccl else 0)
         per_epoch = 2 + per_mb * self.n_mb                 # epoch_prepare + value_stats_sequence
         finalize = 1 + 8 + 1                               # flat map, 8 field gathers, segmented scan
         return finalize + per_epoch * self.w["epochs"]
