@@ -260,8 +260,8 @@ class UpdateEngine:
         self.epoch_stats.zero_()
         self.mb_cursor.zero_()
         n_full = n // self.batch_size
-        # PPOAF_EPOCH_GRAPH: "1" / "0" force it; default: on for a single rank, per-step graphs for R > 1
-        eg = os.environ.get("PPOAF_EPOCH_GRAPH", "1" if mpi_utils.get_num_procs() == 1 else "0")
+        # PPOAF_EPOCH_GRAPH=0 falls back to one graph replay per minibatch
+        eg = os.environ.get("PPOAF_EPOCH_GRAPH", "1")
         if (self.use_graphs and n_full >= 2 and eg == "1"
                 and (mpi_utils.get_num_procs() == 1 or self.peer is not None)):
             self._launch_full_minibatches(ds, n_full)          # ONE graph for all full minibatches of the epoch
