@@ -1,12 +1,16 @@
 // One PPO minibatch as a fixed kernel sequence (reference ppo.py:2292-2468 -> policies/ppo_policy.py:
 // 891-952, 1012-1055), plus the library-wide utilities (error string, device info).
 //
-//   grads:  forward layer l of actor AND critic (one grouped launch per l)  ->  fused loss fwd/bwd
-//           ->  dW/db and dX of layer l of both networks (one grouped launch per l, top layer first)
-//   apply:  [caller all-reduces `grads` when R > 1 -> norm pass]  ->  clip + Adam (one launch)
+//   grads:  forward layer l of actor AND critic (one grouped launch per hidden layer)
+//           ->  fused loss kernel: the two head layers, loss forward/backward, the heads' dX
+//           ->  dW/db and dX of layer l of both networks (one grouped launch per l, top layer first; the heads' dW
+//               rides in the first of them)
+//   apply:  clip + Adam (one launch).  R > 1: the caller runs the fused exchange + clip + Adam kernel of peer.cu
+//           instead (or, on the NCCL fallback, all-reduces `grads` first: then a norm pass precedes Adam).
 //
-// 10 launches per minibatch on one stream.  Every kernel reads the minibatch cursor from device
-// memory, so ONE captured graph serves every full minibatch.
+// 8 launches per minibatch on one stream (10 when the head layers cannot be fused: loss.cu, loss_head_fusable), chained
+// with programmatic dependent launch (common.cuh).  Every kernel reads the minibatch cursor from device memory, so ONE
+// captured graph serves every full minibatch.
 #include <stdarg.h>
 
 #include "internal.h"
