@@ -10,8 +10,11 @@ static inline bool vec4_ok(const float* p, int ld, int contig_extent) {
     return (reinterpret_cast<uintptr_t>(p) % 16 == 0) && (ld % 4 == 0) && (contig_extent % 4 == 0);
 }
 
-// Called from ppoaf_runtime_init so that no attribute call happens inside a stream capture.
+// Called from ppoaf_runtime_init (so that the attribute calls normally happen before any stream capture) and, for
+// callers of the C ABI that never initialise the runtime, lazily by the first launch.
+static bool g_gemm_configured = false;
 void configure_gemm_kernels() {
+    g_gemm_configured = true;
     cudaFuncSetAttribute(grouped_gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, int(kGemmSmemBytes));
     cudaFuncSetAttribute(umma::umma_grouped_gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                          int(umma::kUmmaSmemBytes));
@@ -69,6 +72,7 @@ int GemmGroup::add_backward_w(const float* dZ, const float* X, int ldx, const in
 
 int GemmGroup::launch(const int32_t* cursor, int cursor_stride, cudaStream_t s, int n_mirror, const int64_t* mirror_delta) {
     if (n_tiles == 0) return 0;
+    if (!g_gemm_configured) configure_gemm_kernels();
     args->cursor = cursor;
     args->cursor_stride = cursor_stride;
     args->mirror.n = n_mirror;

@@ -221,7 +221,9 @@ def test_normalize_clip_vs_oracle(n, dim):
 # ----------------------------------------------------------------------------------------- P1/P2
 @pytest.mark.parametrize("dims,act,rows", [([8, 64, 64, 64, 2], "leaky_relu", 512), ([376, 256, 256, 256, 17], "tanh", 512),
                                            ([18, 128, 128, 128, 5], "leaky_relu", 128), ([54, 256, 256, 256, 1], "relu", 130),
-                                           ([4, 128, 128, 128, 2], "leaky_relu", 3), ([5, 3], "tanh", 9)])
+                                           ([4, 128, 128, 128, 2], "leaky_relu", 3), ([5, 3], "tanh", 9),
+                                           # reduction longer than one staged round (K > 512): gathered and plain layers
+                                           ([700, 600, 3], "tanh", 70), ([1030, 40], "relu", 33)])
 def test_mlp_forward_vs_torch_fp32(dims, act, rows, gemm_backend):
     from oracle.update import ACTIVATIONS
     from ppo_and_friends_b200 import _lib, ops
@@ -391,6 +393,48 @@ def test_update_vs_oracle_humanoid_shape(gemm_backend):
         for k, v in obj.state_dict().items():
             np.testing.assert_allclose(v.cpu().numpy(), ref_state[f"{net}/param/{k}"], rtol=1e-4, atol=1e-6, err_msg=k)
     np.testing.assert_allclose(ds.values.cpu().numpy(), host["values"], rtol=1e-4, atol=1e-5)
+
+
+def test_update_vs_oracle_wide_nets_large_batch():
+    """Shapes outside the fused fast paths: hidden 320 / 576 (> 256: the head layers are NOT fused into the loss kernel,
+    the 576-wide layers need two staged rounds of the reduction) and minibatches of 640 rows (backward-w reduces over
+    K = 640 > 512), against the torch-CPU oracle.  Default (FFMA) backend only: with two Adam steps on LeakyReLU nets
+    the 3xTF32 backend's ~1e-6 gradient error exceeds the 1e-6 absolute parameter tolerance on near-zero gradients;
+    its parity is covered by the golden and Humanoid-shaped update tests above."""
+    from oracle.update import OracleUpdater
+    from ppo_and_friends_b200.ppo import PPOUpdateState, _Loader, ppo_batch_train
+    from ppo_and_friends_b200.synthetic import make_rollout
+    ro = make_rollout(seed=78, T=20, E=64, obs_dim=24, act_dim=5, max_ts_per_ep=10, obs_scale=False)
+    torch.manual_seed(6)
+    pol = make_policy(ro, act="leaky_relu", actor_hidden=320, critic_hidden=576, depth=2, lr=3e-4)
+    with torch.no_grad():
+        for a in ro.agents:
+            obs = ro.obs[a].reshape(-1, 24)
+            mu = pol.actor(obs).cpu().numpy()
+            sd = np.maximum(np.log1p(np.exp(-0.5)), 0.01)
+            raw = (mu + sd * np.random.default_rng(2).standard_normal(mu.shape)).astype(np.float32)
+            ro.raw_actions[a] = raw.reshape(ro.T, ro.E, 5)
+            _, lp, _ = pol.evaluate(ro.critic_obs[a].reshape(-1, 24), obs, raw)
+            ro.log_probs[a] = lp.cpu().numpy().reshape(ro.T, ro.E)
+            ro.values[a] = pol.critic(ro.critic_obs[a].reshape(-1, 24)).cpu().numpy().reshape(ro.T, ro.E)
+    ds = run_device_rollout(pol, ro)
+    host = {k: getattr(ds, k).cpu().numpy().copy() for k in ("critic_observations", "observations", "raw_actions",
+                                                               "advantages", "log_probs", "rewards_to_go", "values")}
+    oracle = OracleUpdater({k: v.cpu().numpy() for k, v in pol.actor.state_dict().items()},
+                           {k: v.cpu().numpy() for k, v in pol.critic.state_dict().items()}, "leaky_relu", False, lr=3e-4)
+    state = PPOUpdateState({"pol": pol}, batch_size=640, epochs_per_iter=1)
+    torch.manual_seed(12)
+    ppo_batch_train(state, _Loader(ds, 640), "pol")
+    perm = pol._engine._perm_dev.cpu().numpy()
+    st = oracle.batch_train([host], [perm], 640)
+    sd = state.status_dict["pol"]
+    got = np.array([sd["actor loss"], sd["critic loss"], sd["kl avg"], sd["weighted entropy"]])
+    ref = np.array([st["actor loss"], st["critic loss"], st["kl avg"], st["weighted entropy"]])
+    assert rel_err(got, ref, 1e-3) < 1e-4, (got, ref)
+    ref_state = oracle.state()
+    for net, obj in (("actor", pol.actor), ("critic", pol.critic)):
+        for k, v in obj.state_dict().items():
+            np.testing.assert_allclose(v.cpu().numpy(), ref_state[f"{net}/param/{k}"], rtol=1e-4, atol=1e-6, err_msg=k)
 
 
 # ----------------------------------------------------------------------------------------- P5 / multi-GPU
