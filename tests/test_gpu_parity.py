@@ -398,9 +398,10 @@ def test_update_vs_oracle_humanoid_shape(gemm_backend):
 def test_update_vs_oracle_wide_nets_large_batch():
     """Shapes outside the fused fast paths: hidden 320 / 576 (> 256: the head layers are NOT fused into the loss kernel,
     the 576-wide layers need two staged rounds of the reduction) and minibatches of 640 rows (backward-w reduces over
-    K = 640 > 512), against the torch-CPU oracle.  Default (FFMA) backend only: with two Adam steps on LeakyReLU nets
-    the 3xTF32 backend's ~1e-6 gradient error exceeds the 1e-6 absolute parameter tolerance on near-zero gradients;
-    its parity is covered by the golden and Humanoid-shaped update tests above."""
+    K = 640 > 512), against the torch-CPU oracle.  Default (FFMA) backend only: on the opt-in tcgen05 backend a few
+    parameters of this case missed the `1e-4 rel + 1e-6 abs` bound in round 1 (most differences are ~1e-6; whether the
+    rest is 3xTF32 rounding on near-zero gradients under Adam or a tail-shape problem has not been investigated yet --
+    DESIGN.md section 9).  That backend's parity is covered by the golden and Humanoid-shaped update tests above."""
     from oracle.update import OracleUpdater
     from ppo_and_friends_b200.ppo import PPOUpdateState, _Loader, ppo_batch_train
     from ppo_and_friends_b200.synthetic import make_rollout
