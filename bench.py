@@ -373,6 +373,13 @@ def cpu_reference_sample(w, sample_minibatches=8, seed=1234):
                        f"(python scans, 1 core); t_update={t_upd:.3f}s t_adv={t_adv:.3f}s"), t_adv + t_upd
 
 
+def workload_label(w):
+    """One string for both arms (`config.workload`)."""
+    return (f"{w['name']} (obs {w['Do']}, critic obs {w['Dc']}, act {w['Da'] if not w['n_disc'] else w['n_disc']}, "
+            f"{w['actor_hidden']}/{w['critic_hidden']}-wide MLPs, ts={w['ts']}, E={w['E']} per rank, "
+            f"B={w['B']}, epochs={w['epochs']}, KL early stop off)")
+
+
 def run_reference_arm(args, w):
     rank, world, _ = dist_env()
     if rank != 0:
@@ -388,7 +395,7 @@ def run_reference_arm(args, w):
     line = {"impl": "reference", "metric": "ppo_update_env_steps_per_s", "value": v, "unit": "env-steps/s",
             "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * secs / args.steps,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": w["name"], "note": "oracle port of the reference CPU path on the host cores; "
+            "config": {"workload": workload_label(w), "note": "oracle port of the reference CPU path on the host cores; "
                        "value extrapolated from a bounded sample per step (see cpu_baseline.sample)"},
             "cpu_baseline": res, "e2e": {"value": v, "unit": "env-steps/s", "h2d_bytes_per_step": 0,
                                          "d2h_bytes_per_step": 0}, "gpu_launches": 0}
@@ -440,9 +447,7 @@ def main():
     line = {"metric": "ppo_update_env_steps_per_s", "value": value, "unit": "env-steps/s", "n_gpus": world,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": f"{w['name']} (obs {w['Do']}, critic obs {w['Dc']}, act {w['Da'] if not w['n_disc'] else w['n_disc']}, "
-                                   f"{w['actor_hidden']}/{w['critic_hidden']}-wide MLPs, ts={w['ts']}, E={w['E']} per rank, "
-                                   f"B={w['B']}, epochs={w['epochs']}, KL early stop off)",
+            "config": {"workload": workload_label(w),
                        "per_rank_samples": hp.n, "minibatch_steps_per_step": mb_steps, "us_per_minibatch_step": us_per_mb,
                        "parallelism": f"dp{world}", "l2": "256 MB flush write between timed iterations; ring "
                                                           f"{ring_mb:.0f} MB", "peaks": pk["source"]},
