@@ -18,7 +18,7 @@ from collections import OrderedDict
 import numpy as np
 import torch
 
-from . import _lib, ops
+from . import _lib
 from ._lib import HP, ST, check, load, ptr, stream_ptr
 from .utils import mpi_utils
 from .utils.misc import RunningStatNormalizer

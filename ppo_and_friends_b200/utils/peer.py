@@ -13,7 +13,6 @@ import ctypes as C
 import torch
 import torch.distributed as dist
 
-from .. import _lib
 from .._lib import check, load
 
 

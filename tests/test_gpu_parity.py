@@ -565,7 +565,6 @@ def test_checkpoint_resume_from_reference_state_matches_reference_epoch(tmp_path
     in the reference's checkpoint formats, load it through PPOPolicy.load / RunningStatNormalizer.load_info, run
     epoch 1 on the device and compare with the reference's epoch 1.  Then save and check that the optimizer file loads
     into a real torch.optim.Adam."""
-    import pickle
     name = "upd_gauss"
     g = load_golden(name)
     ro, pol = policy_from_update_golden(g)
