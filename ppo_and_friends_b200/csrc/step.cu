@@ -169,7 +169,9 @@ static int stop_after() { const char* e = getenv("PPOAF_STOP_AFTER"); return e ?
 #endif
 
 extern "C" int ppoaf_ppo_minibatch_grads(const ppoaf_update_cfg* cfg, const ppoaf_update_bufs* b, void* stream) {
-    int launched__ = 0; (void)launched__;
+#ifdef PPOAF_GEMM_TIMING
+    int launched__ = 0;
+#endif
     if (check_cfg(cfg, "ppoaf_ppo_minibatch_grads")) return 1;
     PPOAF_CHECK_ARG(b != nullptr && b->batch >= 1 && b->batch <= b->batch_size && b->n_flat > 0,
                     "ppoaf_ppo_minibatch_grads: bad batch sizes");
