@@ -136,7 +136,7 @@ def run_reference_rollout(pol, ro, tensor_bootstrap=True):
     return out
 
 
-def gen_segments():
+def gen_segments(only=None):
     cases = {
         "seg_single": dict(ro=dict(seed=11, T=48, E=4, obs_dim=3, act_dim=2, max_ts_per_ep=8,
                                    p_term=0.05, p_trunc=0.04), pol={}),
@@ -153,8 +153,19 @@ def gen_segments():
                                    p_term=0.1, p_trunc=0.1), pol=dict(bootstrap_clip=None)),
         "seg_long": dict(ro=dict(seed=17, T=300, E=2, obs_dim=1, act_dim=1, max_ts_per_ep=300,
                                  p_term=0.004, p_trunc=0.0), pol=dict(gamma=0.995, lambd=0.97)),
+        # edge shapes: every step ends its episode (all segments have length 1) ...
+        "seg_len1": dict(ro=dict(seed=18, T=12, E=3, obs_dim=2, act_dim=1, max_ts_per_ep=50,
+                                 p_term=1.0, p_trunc=0.0), pol={}),
+        # ... nothing ever ends: one open segment per env, closed (and bootstrapped) at the end of the rollout ...
+        "seg_open": dict(ro=dict(seed=19, T=25, E=4, obs_dim=2, act_dim=2, max_ts_per_ep=1000,
+                                 p_term=0.0, p_trunc=0.0), pol={}),
+        # ... and every step is cut by max_ts_per_ep = 1 (truncation with bootstrapping on every step)
+        "seg_max1": dict(ro=dict(seed=20, T=10, E=2, obs_dim=2, act_dim=1, max_ts_per_ep=1,
+                                 p_term=0.0, p_trunc=0.0), pol={}),
     }
     for name, c in cases.items():
+        if only is not None and name not in only:
+            continue
         ro = make_rollout(**c["ro"])
         # widen rewards/bootstraps so clipping actually bites in the clip cases
         for a in ro.agents:
@@ -373,6 +384,8 @@ if __name__ == "__main__":
     import sys
     if len(sys.argv) > 1 and sys.argv[1] == "actions":       # only the rollout-action fixtures (added later)
         gen_rollout_actions()
+    elif len(sys.argv) > 1 and sys.argv[1] == "edges":       # only the edge-shape segment fixtures (added later)
+        gen_segments(only=("seg_len1", "seg_open", "seg_max1"))
     else:
         gen_segments()
         gen_stats()

@@ -16,7 +16,8 @@ from helpers import make_policy, policy_kwargs_from_golden, rel_err, run_device_
 
 pytestmark = pytest.mark.gpu
 
-SEG_CASES = ["seg_single", "seg_multi", "seg_bsclip", "seg_nogae", "seg_dynclip", "seg_noclip", "seg_long"]
+SEG_CASES = ["seg_single", "seg_multi", "seg_bsclip", "seg_nogae", "seg_dynclip", "seg_noclip", "seg_long",
+             "seg_len1", "seg_open", "seg_max1"]          # edge shapes: all length-1, never-ending, cut at every step
 
 
 @pytest.fixture(params=["ffma", "tcgen05"])
