@@ -288,3 +288,29 @@ def test_adam_view_state_dict_is_torch_adam_compatible():
     # a fresh optimizer (no step yet) has an empty state, like torch's
     nets4 = PolicyNetworks("cpu", [5, 8, 8, 3], [5, 6, 1], torch.nn.Tanh(), torch.nn.Tanh(), gaussian=True, act_dim=3)
     assert _AdamView(1e-3, nets4.actor).state_dict()["state"] == {}
+
+
+def test_ctypes_structs_match_the_c_header(tmp_path):
+    """The ctypes mirrors in _lib.py must have the layout the C compiler gives the structs of include/ppoaf_b200.h
+    (sizes and the offsets of the fields added last)."""
+    import ctypes as C
+    import shutil
+    import subprocess
+    from ppo_and_friends_b200 import _lib
+    cc = shutil.which("gcc") or shutil.which("cc")
+    if cc is None:
+        pytest.skip("no C compiler")
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    src = tmp_path / "layout.c"
+    src.write_text('#include <stdio.h>\n#include <stddef.h>\n#include "ppoaf_b200.h"\n'
+                   'int main(void) {\n'
+                   '  printf("%zu %zu %zu %zu %zu %zu %zu\\n", sizeof(ppoaf_mlp_desc), sizeof(ppoaf_update_cfg),\n'
+                   '         sizeof(ppoaf_update_bufs), offsetof(ppoaf_update_bufs, n_flat), offsetof(ppoaf_update_bufs, batch),\n'
+                   '         offsetof(ppoaf_update_bufs, n_mirror), offsetof(ppoaf_update_bufs, mirror_delta));\n'
+                   '  return 0;\n}\n')
+    exe = tmp_path / "layout"
+    subprocess.run([cc, "-std=c99", "-I", os.path.join(root, "include"), str(src), "-o", str(exe)], check=True)
+    got = [int(x) for x in subprocess.run([str(exe)], check=True, capture_output=True, text=True).stdout.split()]
+    want = [C.sizeof(_lib.MlpDesc), C.sizeof(_lib.UpdateCfg), C.sizeof(_lib.UpdateBufs), _lib.UpdateBufs.n_flat.offset,
+            _lib.UpdateBufs.batch.offset, _lib.UpdateBufs.n_mirror.offset, _lib.UpdateBufs.mirror_delta.offset]
+    assert got == want, (got, want)
