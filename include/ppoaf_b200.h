@@ -210,6 +210,18 @@ int ppoaf_value_stats_sequence(double* state, const double* mb_val_triples /* [n
 int ppoaf_ppo_minibatch_grads(const ppoaf_update_cfg* cfg, const ppoaf_update_bufs* bufs, void* stream);
 int ppoaf_ppo_minibatch_apply(const ppoaf_update_cfg* cfg, const ppoaf_update_bufs* bufs, void* stream);
 
+/* The same minibatch step(s) as ONE persistent launch (fused_step.cu): n_steps consecutive minibatches of bufs->batch rows,
+ * starting at *mb_cursor, each = forward (tcgen05 3xTF32 tiles) -> heads + loss -> backward -> clip + Adam, the phases
+ * separated by grid barriers instead of launch boundaries; mb_cursor and adam_step advance by n_steps.  Replaces the loop
+ * body of PPO._ppo_batch_train (ppo.py:2292-2468) for a whole epoch.  Supported when ppoaf_ppo_fused_supported(cfg) != 0
+ * (equal depth >= 2 and activation of actor and critic, head layers fusable into the loss phase: hidden width <= 256 and
+ * a multiple of 4, <= 24 actor outputs, no value clipping; single rank); other configurations use
+ * ppoaf_ppo_minibatch_grads / _apply.  Workspace: ppoaf_ppo_fused_workspace_bytes, zero-initialised once (it holds the
+ * grid-barrier words, which persist from launch to launch).  n_steps > 1 requires bufs->batch == bufs->batch_size. */
+int    ppoaf_ppo_fused_supported(const ppoaf_update_cfg* cfg);
+size_t ppoaf_ppo_fused_workspace_bytes(const ppoaf_update_cfg* cfg, int32_t max_batch);
+int    ppoaf_ppo_fused_steps(const ppoaf_update_cfg* cfg, const ppoaf_update_bufs* bufs, int32_t n_steps, void* stream);
+
 /* Forward only (P1/P2; also rollout-time inference): y = MLP(x[idx]) for
  * n_rows rows; idx may be NULL (identity).  softmax applied when `softmax_out` (Discrete actor,
  * networks/distributions.py:1045). */

@@ -79,6 +79,9 @@ _SIGNATURES = {
     "ppoaf_value_stats_sequence": (C.c_int, [_P, _P, C.c_int32, C.c_int32, C.c_float, _P, _P]),
     "ppoaf_ppo_minibatch_grads": (C.c_int, [C.POINTER(UpdateCfg), C.POINTER(UpdateBufs), _P]),
     "ppoaf_ppo_minibatch_apply": (C.c_int, [C.POINTER(UpdateCfg), C.POINTER(UpdateBufs), _P]),
+    "ppoaf_ppo_fused_supported": (C.c_int, [C.POINTER(UpdateCfg)]),
+    "ppoaf_ppo_fused_workspace_bytes": (C.c_size_t, [C.POINTER(UpdateCfg), C.c_int32]),
+    "ppoaf_ppo_fused_steps": (C.c_int, [C.POINTER(UpdateCfg), C.POINTER(UpdateBufs), C.c_int32, _P]),
     "ppoaf_mlp_forward_workspace_bytes": (C.c_size_t, [C.POINTER(MlpDesc), C.c_int32]),
     "ppoaf_mlp_forward": (C.c_int, [C.POINTER(MlpDesc), _P, _P, _P, C.c_int32, C.c_int, _P, _P, C.c_size_t, _P]),
     "ppoaf_head_evaluate": (C.c_int, [C.c_int32, _P, C.c_int32, _P, C.c_float, _P, C.c_int32, C.c_int32, _P, _P, _P]),

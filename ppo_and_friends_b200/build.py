@@ -18,8 +18,8 @@ ROOT = os.path.dirname(HERE)
 LIB_PATH = os.path.join(CSRC, "libppoaf_b200.so")
 STAMP = os.path.join(CSRC, ".build_stamp")
 
-SOURCES = ["segscan.cu", "gather.cu", "stats.cu", "mlp.cu", "loss.cu", "optim.cu", "step.cu", "peer.cu"]
-HEADERS = ["common.cuh", "mlp.cuh", "umma.cuh", "internal.h", os.path.join(ROOT, "include", "ppoaf_b200.h")]
+SOURCES = ["segscan.cu", "gather.cu", "stats.cu", "mlp.cu", "loss.cu", "optim.cu", "step.cu", "peer.cu", "fused_step.cu"]
+HEADERS = ["common.cuh", "mlp.cuh", "umma.cuh", "loss_common.cuh", "internal.h", os.path.join(ROOT, "include", "ppoaf_b200.h")]
 
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",

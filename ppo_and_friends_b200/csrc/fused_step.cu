@@ -1,0 +1,1157 @@
+// The PPO minibatch step as ONE persistent kernel (reference ppo.py:2292-2468 -> policies/ppo_policy.py:891-952,
+// 1012-1055): every minibatch of an epoch runs inside a single launch, one CTA per SM, the phases of a step separated
+// by a grid barrier (~0.5 us) instead of a launch boundary (~7 us per dependent launch in the launch-chain path,
+// step.cu).  Per step (L = Linear layers per network, actor and critic side by side in every phase):
+//
+//   FWD l = 0 .. L-2     Y = act(X[idx] W^T + b)                    tcgen05 tiles 128 x bn, 3xTF32
+//   LOSS                 the two head layers, PPO loss forward/backward, the heads' dX   (one warp per sample)
+//   BWD_X l = L-2 .. 1   dZ_l = (dZ_{l+1} W) * act'(X_l)            tcgen05 tiles 128 x bn
+//   BWD_W                dW_l = dZ_{l+1}^T X_l, db_l, per-tile sums of squares (all layers of both networks)
+//   ADAM                 gradient-norm clip + Adam on this CTA's slice, counters
+//
+// GEMM tiles: A (the operand indexed by the 128 tile rows) and B are staged global -> registers -> shared memory
+// by 8 warps, which split every fp32 element into hi = tf32(x), lo = tf32(x - hi) on the way (3xTF32:
+// D += hi*hi + hi*lo + lo*hi, fp32 accumulation in TMEM, fp32-grade products); a ninth warp issues
+// tcgen05.mma (cta_group::1, kind::tf32) from one lane and commits to mbarriers; the 8 warps read the accumulator back
+// with tcgen05.ld for the fused epilogues (bias + activation; activation derivative; bias gradient + sum of squares).
+// bn (16 / 32 / 64) is chosen per phase so that a phase has about one tile per SM.
+// Everything a phase reads that another CTA wrote in an earlier phase is loaded with ld.global.cg (L2), never through L1.
+#define PPOAF_HELPERS_ONLY
+#include "umma.cuh"
+#include "loss_common.cuh"
+
+namespace ppoaf {
+namespace fused {
+
+using umma::mbar_init;
+using umma::mbar_wait;
+using umma::smem_u32;
+using umma::tf32_rna;
+
+constexpr int kFM = 128, kFK = 32, kFStages = 4;
+constexpr int kStageThreads = 256, kFThreads = kStageThreads + 128;   // 8 staging warps + the MMA warpgroup (warp 8 issues)
+constexpr int kStageRegs = 224, kMmaRegs = 56;                        // setmaxnreg: 256 x 224 + 128 x 56 = 168 x 384
+constexpr int kMaxBN = 64;
+constexpr int kATile = kFM * kFK, kBTile = kMaxBN * kFK;                 // floats
+constexpr int kFStageFloats = 2 * kATile + 2 * kBTile;                   // A_hi | A_lo | B_hi | B_lo = 48 KB
+constexpr size_t kFusedSmemBytes = size_t(kFStages) * kFStageFloats * sizeof(float) + 1024;
+constexpr int kFTmemCols = 64;
+constexpr int kMaxProblems = 6 * PPOAF_MAX_LAYERS;
+constexpr int kMaxPhases = 2 * PPOAF_MAX_LAYERS + 2;
+constexpr int kBarStride = 8;                                            // one 32-byte sector per CTA arrival word
+constexpr int kMaxGrid = 256;
+
+enum { PH_FWD = 0, PH_BWD_X, PH_BWD_W, PH_LOSS, PH_ADAM };
+
+struct PhaseDesc { int type, first, count, n_tiles; };
+
+struct FusedPlan {
+    int n_phases, n_problems, n_steps, batch;
+    int loss_finalize_phase;               // phase at whose start the last CTA folds the loss partials
+    int batch_size;                        // cursor stride of the permutation
+    PhaseDesc ph[kMaxPhases];
+    GemmProblem p[kMaxProblems];
+    LossArgs loss;
+    MirrorSet mirror;
+    float* params; const float* grads; float* m; float* v;
+    int64_t n_actor, n_total;
+    const double* sq_a; int n_sq_a;
+    const double* sq_c; int n_sq_c;
+    const double* hp;
+    int64_t* adam_step;
+    int32_t* mb_cursor;
+    uint32_t* bar;                         // [0 .. grid*kBarStride): arrival words; [kMaxGrid*kBarStride]: epoch of the last launch
+};
+
+__device__ __forceinline__ void st_release_gpu(uint32_t* p, uint32_t v) {
+    asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+__device__ __forceinline__ uint32_t ld_acquire_gpu(const uint32_t* p) {
+    uint32_t v;
+    asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void bar_stage() { asm volatile("bar.sync 1, %0;" ::"n"(kStageThreads) : "memory"); }
+
+// Grid barrier (all CTAs are co-resident: cooperative launch, one CTA per SM).  CTA b publishes `epoch` in its own
+// word; thread t of every CTA polls word t, so the release costs one L2 round trip after the last arrival and no
+// contended atomic.
+__device__ __forceinline__ void grid_sync(uint32_t* arrive, uint32_t epoch) {
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        __threadfence();
+        st_release_gpu(arrive + kBarStride * blockIdx.x, epoch);
+    }
+    if (threadIdx.x < gridDim.x) {
+        while (int32_t(ld_acquire_gpu(arrive + kBarStride * threadIdx.x) - epoch) < 0) {}
+    }
+    __syncthreads();
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+}
+
+// 4 consecutive floats (zero beyond n_valid) straight from L2
+__device__ __forceinline__ float4 ldcg4(const float* __restrict__ p, int n_valid, bool vec) {
+    if (n_valid <= 0) return make_float4(0.f, 0.f, 0.f, 0.f);
+    if (vec && n_valid >= 4) return __ldcg(reinterpret_cast<const float4*>(p));
+    float4 v;
+    v.x = __ldcg(p);
+    v.y = n_valid > 1 ? __ldcg(p + 1) : 0.f;
+    v.z = n_valid > 2 ? __ldcg(p + 2) : 0.f;
+    v.w = n_valid > 3 ? __ldcg(p + 3) : 0.f;
+    return v;
+}
+
+// Per-thread staging plan of one operand tile of R rows/outputs (R = 128 for A; 16 / 32 / 64 for B) and 32 k's:
+//   K-major  (RC): 16-byte chunk (row = tid/8 + 32 i, kq = tid%8)            global P[row(out0+row)*ld + k0 + 4 kq]
+//   MN-major (OC): 16-byte chunk (k = tid/(R/4) + (1024/R) i, rq = tid%(R/4))  global P[row(k0+k)*ld + out0 + 4 rq]
+// shared-memory layouts as in umma.cuh (SWIZZLE_128B K-major; SWIZZLE_128B_BASE32B MN-major)
+template <int MAXCH, bool RC>
+struct FStager {
+    int dst[MAXCH];
+    const float* src[MAXCH];
+    int lim[MAXCH];
+    int k_of[MAXCH];
+    const int64_t* idx;
+    const float* P;
+    int ld, o_off, kq4, n_ch;
+    bool vec;
+
+    __device__ __forceinline__ void plan(int tid, int R, const float* P_, int ld_, const int64_t* idx_, int out0, int out_ext,
+                                         int k_ext, bool vec_) {
+        P = P_; ld = ld_; idx = idx_; vec = vec_;
+        n_ch = 0;
+        o_off = 0; kq4 = 0;
+#pragma unroll
+        for (int i = 0; i < MAXCH; ++i) {
+            dst[i] = 0; src[i] = P_; lim[i] = 0; k_of[i] = 0;
+            if constexpr (RC) {
+                const int row = tid / 8 + 32 * i, kq = tid % 8;
+                kq4 = kq * 4;
+                if (row < R) {
+                    n_ch = i + 1;
+                    dst[i] = row * 32 + ((kq ^ (row & 7)) * 4);
+                    const int grow = out0 + row;
+                    if (grow < out_ext) {
+                        const int64_t r = idx ? idx[grow] : int64_t(grow);
+                        src[i] = P + r * ld + kq4;
+                        lim[i] = k_ext;
+                    }
+                }
+            } else {
+                const int q = R / 4;                                   // float4 chunks per k-row
+                const int k = tid / q + (kStageThreads / q) * i, rq = tid % q;
+                if (k < kFK) {
+                    n_ch = i + 1;
+                    dst[i] = (rq / 8) * 1024 + (k / 4) * 128 + (k % 4) * 32 + ((((rq / 2) % 4) ^ (k % 4)) * 8) + (rq % 2) * 4;
+                    k_of[i] = k;
+                    o_off = out0 + rq * 4;
+                    lim[i] = out_ext - o_off;
+                    src[i] = P + int64_t(k) * ld + o_off;
+                }
+            }
+        }
+    }
+    __device__ __forceinline__ void load(float4 (&v)[MAXCH], int k0, int k_ext) const {
+#pragma unroll
+        for (int i = 0; i < MAXCH; ++i) {
+            if (i < n_ch) {
+                if constexpr (RC) {
+                    v[i] = ldcg4(src[i] + k0, lim[i] - (k0 + kq4), vec);
+                } else {
+                    const int k = k0 + k_of[i];
+                    if (k < k_ext) {
+                        const float* p = idx ? P + idx[k] * ld + o_off : src[i] + int64_t(k0) * ld;
+                        v[i] = ldcg4(p, lim[i], vec);
+                    } else {
+                        v[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+                    }
+                }
+            }
+        }
+    }
+    __device__ __forceinline__ void store(const float4 (&v)[MAXCH], float* hi_tile, float* lo_tile) const {
+#pragma unroll
+        for (int i = 0; i < MAXCH; ++i) {
+            if (i < n_ch) {
+                float4 h, l;
+                h.x = tf32_rna(v[i].x); l.x = tf32_rna(v[i].x - h.x);
+                h.y = tf32_rna(v[i].y); l.y = tf32_rna(v[i].y - h.y);
+                h.z = tf32_rna(v[i].z); l.z = tf32_rna(v[i].z - h.z);
+                h.w = tf32_rna(v[i].w); l.w = tf32_rna(v[i].w - h.w);
+                *reinterpret_cast<float4*>(hi_tile + dst[i]) = h;
+                *reinterpret_cast<float4*>(lo_tile + dst[i]) = l;
+            }
+        }
+    }
+};
+
+__device__ __forceinline__ void tmem_ld8(uint32_t taddr, uint32_t (&r)[8]) {
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];\n"
+                 : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7])
+                 : "r"(taddr));
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+
+// One output tile.  Warps 0..7 stage operands and run the epilogue; warp 8 (one lane) issues the MMAs.  gchunk / gtile
+// are running counters (identical in every thread) from which the stage slots and mbarrier parities follow, so the
+// pipeline state carries over from tile to tile and phase to phase.
+//   full[s] : 8 arrivals (one per staging warp, after its stores + proxy fence)  -> stage s may be read by the MMAs
+//   free[s] : tcgen05.commit                                                     -> stage s may be overwritten
+//   acc     : tcgen05.commit after the last chunk                                 -> accumulator complete
+// MMA issuer (one lane of warp 8) for one tile: waits for every staged chunk, issues the 3xTF32 MMAs, commits.
+__device__ __forceinline__ void ftile_mma(const GemmProblem& g, bool a_rc, bool b_rc, float* smem, uint64_t* bars, uint32_t tmem,
+                                          uint32_t& gchunk) {
+    const int bn = g.bn;
+    uint64_t* bar_full = bars;
+    uint64_t* bar_free = bars + kFStages;
+    uint64_t* bar_acc = bars + 2 * kFStages;
+    const int n_chunks = (g.K + kFK - 1) / kFK;
+    const uint32_t c0 = gchunk;
+    gchunk += uint32_t(n_chunks);
+    const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((a_rc ? 0u : 1u) << 15) | ((b_rc ? 0u : 1u) << 16) |
+                           (uint32_t(bn >> 3) << 17) | (uint32_t(kFM >> 4) << 24);
+    const uint64_t da0 = a_rc ? umma::desc_base<true>() : umma::desc_base<false>();
+    const uint64_t db0 = b_rc ? umma::desc_base<true>() : umma::desc_base<false>();
+    const uint64_t ua = a_rc ? umma::kstep_units<true>() : umma::kstep_units<false>();
+    const uint64_t ub = b_rc ? umma::kstep_units<true>() : umma::kstep_units<false>();
+    for (int c = 0; c < n_chunks; ++c) {
+        const uint32_t gc = c0 + uint32_t(c);
+        const int s = int(gc % kFStages);
+        mbar_wait(&bar_full[s], (gc / kFStages) & 1u);
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        const uint32_t st = smem_u32(smem + s * kFStageFloats);
+        const uint64_t a_hi = da0 | uint64_t((st >> 4) & 0x3FFF);
+        const uint64_t a_lo = da0 | uint64_t(((st + kATile * 4) >> 4) & 0x3FFF);
+        const uint64_t b_hi = db0 | uint64_t(((st + 2 * kATile * 4) >> 4) & 0x3FFF);
+        const uint64_t b_lo = db0 | uint64_t(((st + (2 * kATile + kBTile) * 4) >> 4) & 0x3FFF);
+#pragma unroll
+        for (uint32_t ks = 0; ks < kFK / 8; ++ks) {
+            const uint64_t oa = ks * ua, ob = ks * ub;
+            umma::mma_tf32(tmem, a_hi + oa, b_hi + ob, idesc, (c > 0 || ks > 0) ? 1u : 0u);
+            umma::mma_tf32(tmem, a_hi + oa, b_lo + ob, idesc, 1u);
+            umma::mma_tf32(tmem, a_lo + oa, b_hi + ob, idesc, 1u);
+        }
+        umma::umma_commit(&bar_free[s]);
+    }
+    umma::umma_commit(bar_acc);
+}
+
+template <bool A_RC, bool B_RC, int EPI>
+__device__ __forceinline__ void ftile(const GemmProblem& g, int tile, int64_t idx_off, const MirrorSet& mir, float* smem,
+                                      uint64_t* bars, uint32_t tmem, uint32_t& gchunk, uint32_t& gtile, double* s_sq) {
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int bn = g.bn;
+    const int m0 = (tile / g.tiles_n) * kFM, n0 = (tile % g.tiles_n) * bn;
+    uint64_t* bar_full = bars;
+    uint64_t* bar_free = bars + kFStages;
+    uint64_t* bar_acc = bars + 2 * kFStages;
+    const int n_chunks = (g.K + kFK - 1) / kFK;
+    const uint32_t c0 = gchunk, acc_parity = gtile & 1u;
+    gchunk += uint32_t(n_chunks);
+    gtile += 1u;
+
+    // ------------------------------ staging warps ------------------------------
+    const int64_t* idxA = g.idxA ? g.idxA + idx_off : nullptr;
+    const int64_t* idxB = g.idxB ? g.idxB + idx_off : nullptr;
+    constexpr int NA = 4, NB = 2;
+    FStager<NA, A_RC> sa;
+    FStager<NB, B_RC> sb;
+    sa.plan(tid, kFM, g.A, g.lda, idxA, m0, g.M, g.K, (g.flavour & 2) != 0);
+    sb.plan(tid, bn, g.B, g.ldb, idxB, n0, g.N, g.K, (g.flavour & 1) != 0);
+    float4 va[2][NA], vb[2][NB];                    // two register sets: chunk c+2 is in flight while chunk c+1 waits
+    float colsum[4] = {0.f, 0.f, 0.f, 0.f};       // EPI_BWD_W: bias gradient = column sums of the A operand (dZ)
+
+    sa.load(va[0], 0, g.K);
+    sb.load(vb[0], 0, g.K);
+    if (n_chunks > 1) {
+        sa.load(va[1], kFK, g.K);
+        sb.load(vb[1], kFK, g.K);
+    }
+
+    // epilogue operands are fetched now, so their latency hides behind the main loop
+    const int q = warp & 3, h = warp >> 2;
+    const int half = bn >> 1;                       // columns per warp: 8, 16 or 32
+    const int m = m0 + q * 32 + lane;
+    const int nb = n0 + h * half;
+    const bool vec_out = (g.ldc % 4 == 0) && (reinterpret_cast<uintptr_t>(g.C) % 16 == 0);
+    float4 epi[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+        epi[j] = make_float4(0.f, 0.f, 0.f, 0.f);
+        const int n = nb + 4 * j;
+        if (4 * j < half) {
+            if constexpr (EPI == EPI_FWD) {
+                if (n < g.N) epi[j] = ldcg4(g.bias + n, g.N - n, vec_out);
+            }
+            if constexpr (EPI == EPI_BWD_X) {
+                if (n < g.N && m < g.M) epi[j] = ldcg4(g.aux + int64_t(m) * g.ldaux + n, g.N - n, vec_out && g.ldaux % 4 == 0);
+            }
+        }
+    }
+
+    auto stage_chunk = [&](int c, float4 (&a_regs)[NA], float4 (&b_regs)[NB]) {
+        const uint32_t gc = c0 + uint32_t(c);
+        const int s = int(gc % kFStages);
+        float* st = smem + s * kFStageFloats;
+        if (gc >= uint32_t(kFStages)) mbar_wait(&bar_free[s], (gc / kFStages - 1u) & 1u);   // the MMAs of chunk gc - kFStages have read it
+        sa.store(a_regs, st, st + kATile);
+        sb.store(b_regs, st + 2 * kATile, st + 2 * kATile + kBTile);
+        if constexpr (EPI == EPI_BWD_W) {
+#pragma unroll
+            for (int i = 0; i < NA; ++i) {
+                colsum[0] += a_regs[i].x; colsum[1] += a_regs[i].y; colsum[2] += a_regs[i].z; colsum[3] += a_regs[i].w;
+            }
+        }
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy stores -> visible to the tensor core
+        __syncwarp();
+        if (lane == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(&bar_full[s])) : "memory");
+        if (c + 2 < n_chunks) {
+            sa.load(a_regs, (c + 2) * kFK, g.K);
+            sb.load(b_regs, (c + 2) * kFK, g.K);
+        }
+    };
+    for (int c = 0; c < n_chunks; c += 2) {
+        stage_chunk(c, va[0], vb[0]);
+        if (c + 1 < n_chunks) stage_chunk(c + 1, va[1], vb[1]);
+    }
+    mbar_wait(bar_acc, acc_parity);
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+
+    // ---- epilogue: warp w reads TMEM lanes 32 (w % 4) .. +31, columns half (w / 4) .. +half-1, 8 columns at a time ----
+    float sq = 0.f;
+    float* crow = g.C + int64_t(m) * g.ldc;
+    const int act = g.act;
+#pragma unroll
+    for (int j8 = 0; j8 < kMaxBN / 2; j8 += 8) {
+        if (j8 >= half) break;                      // warp-uniform
+        uint32_t r[8];
+        tmem_ld8(tmem + (uint32_t(q * 32) << 16) + uint32_t(h * half + j8), r);
+        if (m < g.M) {
+#pragma unroll
+            for (int jj = 0; jj < 2; ++jj) {
+                const int n = nb + j8 + 4 * jj;
+                const float4 e4 = epi[(j8 >> 2) + jj];
+                const float ev[4] = {e4.x, e4.y, e4.z, e4.w};
+                float o[4];
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    float v = __uint_as_float(r[4 * jj + j]);
+                    if constexpr (EPI == EPI_FWD) v = act_fwd_fast(v + ev[j], act);
+                    if constexpr (EPI == EPI_BWD_X) v *= act_bwd_from_out(ev[j], act);
+                    if constexpr (EPI == EPI_BWD_W) { if (n + j < g.N) sq = fmaf(v, v, sq); }
+                    o[j] = v;
+                }
+                if (vec_out && n + 3 < g.N) {
+                    const float4 o4 = make_float4(o[0], o[1], o[2], o[3]);
+                    *reinterpret_cast<float4*>(crow + n) = o4;
+                    if constexpr (EPI == EPI_BWD_W) mirror_store(mir, reinterpret_cast<float4*>(crow + n), o4);
+                } else {
+#pragma unroll
+                    for (int j = 0; j < 4; ++j)
+                        if (n + j < g.N) {
+                            crow[n + j] = o[j];
+                            if constexpr (EPI == EPI_BWD_W) mirror_store(mir, crow + n + j, o[j]);
+                        }
+                }
+            }
+        }
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");   // the next tile's MMAs overwrite the accumulator
+
+    if constexpr (EPI == EPI_BWD_W) {
+        // bias gradient: thread (warp w, lane l) summed rows k = w + 8 i of A columns 4 l .. 4 l + 3 (MN-major A: rq = tid % 32)
+        float* red = smem;                                     // pipeline memory is idle now: [8 warps][128]
+        bar_stage();
+#pragma unroll
+        for (int j = 0; j < 4; ++j) red[warp * kFM + lane * 4 + j] = colsum[j];
+        const double w = warp_sum(double(sq));
+        bar_stage();
+        float db = 0.f;
+        if (tid < kFM) {
+#pragma unroll
+            for (int k = 0; k < kStageThreads / 32; ++k) db += red[k * kFM + tid];
+            if (n0 == 0 && g.dbias && m0 + tid < g.M) {
+                g.dbias[m0 + tid] = db;
+                mirror_store(mir, g.dbias + m0 + tid, db);
+            }
+        }
+        const double wdb = warp_sum((n0 == 0 && tid < kFM && m0 + tid < g.M) ? double(db) * double(db) : 0.0);
+        if (lane == 0) s_sq[warp] = w + wdb;
+        bar_stage();
+        if (tid == 0 && g.sq_out) {
+            double t = 0.0;
+#pragma unroll
+            for (int k = 0; k < kStageThreads / 32; ++k) t += s_sq[k];
+            g.sq_out[tile] = t;
+        }
+        // the generic-proxy writes to `red` must not be overtaken by the next tile's staging stores: same proxy, program
+        // order per thread + the barriers above order them; the async proxy only reads after the next full[] arrival
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// LOSS phase: one warp per sample, samples dealt round-robin over CTAs so that every SM holds 3-4 of a 512-row
+// minibatch.  Head layers, loss and the heads' dX as in ppo_loss_kernel<true> (loss.cu); the per-CTA partial sums are
+// folded by the last CTA at the start of the next phase (loss_finalize).
+__device__ __forceinline__ void loss_phase(const LossArgs& a, int cur, float* s_dyn, float* s_sd, float* s_dsd,
+                                           double (*s_red)[kPartialStride]) {
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int gl = lane;
+    const float inv_b = 1.0f / float(a.batch);
+    const float w_ent = float(a.hparams[PPOAF_HP_ENTROPY_WEIGHT]);
+    const float clip_lo = float(1.0 - a.hparams[PPOAF_HP_SURR_CLIP]), clip_hi = float(1.0 + a.hparams[PPOAF_HP_SURR_CLIP]);
+    const bool gaussian = a.head == PPOAF_HEAD_GAUSSIAN_TANH;
+    const int prows = (a.pred_dim + kPB - 1) / kPB * kPB;
+    const int ldw = a.Ha + 4;
+    float* s_wa = s_dyn;                                             // [prows][ldw]
+    float* s_wc = s_wa + prows * ldw;                                // [Hc]
+    float* s_b = s_wc + a.Hc;                                        // [pred + 1]
+    float* s_pred = s_b + ((a.pred_dim + 1 + 3) & ~3);               // [8 warps][kFusedPredLd]
+    float* s_dpred = s_pred + (kStageThreads / 32) * kFusedPredLd;
+
+    // head weights of both networks (written by the ADAM phase of the previous step: L2 loads)
+    {
+        const int qa = a.Ha / 4;
+        for (int t = tid; t < prows * qa; t += kStageThreads) {
+            const int row = t / qa, c4 = t - row * qa;
+            const float4 w = row < a.pred_dim ? __ldcg(reinterpret_cast<const float4*>(a.W_actor + int64_t(row) * a.Ha + 4 * c4))
+                                              : make_float4(0.f, 0.f, 0.f, 0.f);
+            *reinterpret_cast<float4*>(s_wa + row * ldw + 4 * c4) = w;
+        }
+        for (int t = tid; t < a.Hc / 4; t += kStageThreads)
+            *reinterpret_cast<float4*>(s_wc + 4 * t) = __ldcg(reinterpret_cast<const float4*>(a.W_critic + 4 * t));
+        if (tid < a.pred_dim) s_b[tid] = __ldcg(a.b_actor + tid);
+        if (tid == 0) s_b[a.pred_dim] = __ldcg(a.b_critic);
+        if (gaussian && tid < a.act_dim) {
+            const float ls = __ldcg(a.log_std + tid);
+            const float sp = softplus_torch(ls);
+            s_sd[tid] = fmaxf(sp, a.min_std);
+            const float sig = ls > 20.f ? 1.f : 1.f / (1.f + expf(-ls));
+            s_dsd[tid] = sp > a.min_std ? sig : (sp == a.min_std ? 0.5f * sig : 0.f);
+        }
+    }
+    float adv_mu = 0.f, adv_sd = 1.f, val_mu = 0.f, val_sd = 1.f;    // this minibatch's normalisation constants
+    if (a.normalize_adv) { adv_mu = a.mb_adv_stats[2 * cur]; adv_sd = a.mb_adv_stats[2 * cur + 1]; }
+    if (a.normalize_values) { val_mu = a.mb_val_stats[2 * cur]; val_sd = a.mb_val_stats[2 * cur + 1]; }
+    const int64_t* idx = a.perm + int64_t(cur) * a.batch_size;
+    bar_stage();
+
+    double tot_sc[kLossScalars];
+    double tot_dsd[kPerLane];
+#pragma unroll
+    for (int k = 0; k < kLossScalars; ++k) tot_sc[k] = 0.0;
+#pragma unroll
+    for (int k = 0; k < kPerLane; ++k) tot_dsd[k] = 0.0;
+
+    for (int i = warp * int(gridDim.x) + int(blockIdx.x); i < a.batch; i += (kStageThreads / 32) * int(gridDim.x)) {
+        const int64_t j = idx[i];
+        const int64_t nxt = int64_t(cur + 1) * a.batch_size + i;
+        const int64_t jn = (a.pf_rows[0] && nxt < a.n_flat) ? a.perm[nxt] : -1;
+        float adv = a.advantages[j];
+        const float lp_old = a.log_probs[j];
+        float target = a.rewards_to_go[j];
+        float4 ha[kFusedMaxChunks], hc[kFusedMaxChunks];
+        const float* hra = a.h_actor + int64_t(i) * a.Ha + 4 * gl;
+        const float* hrc = a.h_critic + int64_t(i) * a.Hc + 4 * gl;
+#pragma unroll
+        for (int c = 0; c < kFusedMaxChunks; ++c) {
+            const int col = 4 * (gl + kG * c);
+            ha[c] = col < a.Ha ? __ldcg(reinterpret_cast<const float4*>(hra + 4 * kG * c)) : make_float4(0.f, 0.f, 0.f, 0.f);
+            hc[c] = col < a.Hc ? __ldcg(reinterpret_cast<const float4*>(hrc + 4 * kG * c)) : make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+        if (jn >= 0) {   // pull the NEXT minibatch's observation rows into L2 while this step's backward pass runs
+            const char* r0 = reinterpret_cast<const char*>(a.pf_rows[0]) + jn * a.pf_row_bytes[0];
+            const char* r1 = reinterpret_cast<const char*>(a.pf_rows[1]) + jn * a.pf_row_bytes[1];
+            for (int o = gl * 128; o < a.pf_row_bytes[0]; o += kG * 128) asm volatile("prefetch.global.L2 [%0];" ::"l"(r0 + o));
+            for (int o = gl * 128; o < a.pf_row_bytes[1]; o += kG * 128) asm volatile("prefetch.global.L2 [%0];" ::"l"(r1 + o));
+        }
+        float sc[kLossScalars];
+#pragma unroll
+        for (int k = 0; k < kLossScalars; ++k) sc[k] = 0.f;
+        float dsd[kPerLane];
+#pragma unroll
+        for (int k = 0; k < kPerLane; ++k) dsd[k] = 0.f;
+        if (a.normalize_adv) adv = (adv - adv_mu) / adv_sd;
+        if (a.normalize_values) target = (target - val_mu) / val_sd;
+
+        // ---- head layers, forward ----
+        float v_fused = 0.f;
+        float acc[kFusedMaxPred];
+#pragma unroll
+        for (int d = 0; d < kFusedMaxPred; ++d) acc[d] = 0.f;
+#pragma unroll
+        for (int c = 0; c < kFusedMaxChunks; ++c) {
+            const int col = 4 * (gl + kG * c);
+            if (col < a.Ha) {
+#pragma unroll
+                for (int db = 0; db < kFusedMaxPred / kPB; ++db) {
+                    if (db * kPB < a.pred_dim) {
+                        float4 w[kPB];
+#pragma unroll
+                        for (int e = 0; e < kPB; ++e) w[e] = *reinterpret_cast<const float4*>(s_wa + (db * kPB + e) * ldw + col);
+#pragma unroll
+                        for (int e = 0; e < kPB; ++e)
+                            acc[db * kPB + e] = fmaf(ha[c].x, w[e].x, fmaf(ha[c].y, w[e].y, fmaf(ha[c].z, w[e].z,
+                                                fmaf(ha[c].w, w[e].w, acc[db * kPB + e]))));
+                    }
+                }
+            }
+            if (col < a.Hc) {
+                const float4 w = *reinterpret_cast<const float4*>(s_wc + col);
+                v_fused = fmaf(hc[c].x, w.x, fmaf(hc[c].y, w.y, fmaf(hc[c].z, w.z, fmaf(hc[c].w, w.w, v_fused))));
+            }
+        }
+        float v32[32];
+#pragma unroll
+        for (int d = 0; d < 32; ++d) v32[d] = d < kFusedMaxPred ? acc[d] : (d == kFusedMaxPred ? v_fused : 0.f);
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            const bool up = (lane & o) != 0;
+#pragma unroll
+            for (int k = 0; k < o; ++k) {
+                const float send = up ? v32[k] : v32[k + o];
+                const float keep = up ? v32[k + o] : v32[k];
+                v32[k] = keep + __shfl_xor_sync(kFull, send, o);
+            }
+        }
+        v_fused = __shfl_sync(kFull, v32[0], kFusedMaxPred) + s_b[a.pred_dim];
+        if (gl < a.pred_dim) s_pred[warp * kFusedPredLd + gl] = v32[0] + s_b[gl];
+        __syncwarp();
+        const float v = v_fused;
+        if (gl == 0) a.values[j] = v;                                 // dataset.values[batch_idxs] = values (ppo.py:2340)
+        float bad_value = isnan(v) ? 1.f : 0.f;
+
+        const float* pred = s_pred + warp * kFusedPredLd;
+        float* dpred = a.d_actor_out + int64_t(i) * a.pred_dim;
+        float* sdp = s_dpred + warp * kFusedPredLd;
+        actor_head_loss<true>(a, gaussian, true, gl, j, pred, dpred, sdp, s_sd, adv, lp_old, inv_b, w_ent, clip_lo, clip_hi, sc,
+                              dsd, bad_value);
+
+        // ---- critic ----
+        float dv1 = 0.f;
+        sc[LS_CRITIC] = critic_term(v, target, a.use_huber, dv1);
+        if (gl != 0) sc[LS_CRITIC] = 0.f;
+        if (gl == 0) a.d_critic_out[i] = dv1 * inv_b;
+        const float bad_any = group_max(bad_value);
+        sc[LS_BAD_VALUE] = gl == 0 ? bad_any : 0.f;
+
+        // ---- head layers, backward: dX times the activation derivative of the layer below ----
+        __syncwarp();
+        float dp[kFusedMaxPred];
+#pragma unroll
+        for (int d = 0; d < kFusedMaxPred; ++d) dp[d] = d < a.pred_dim ? sdp[d] : 0.f;
+        const float gv = dv1 * inv_b;
+        float* dza = a.dz_actor + int64_t(i) * a.Ha + 4 * gl;
+        float* dzc = a.dz_critic + int64_t(i) * a.Hc + 4 * gl;
+#pragma unroll
+        for (int c = 0; c < kFusedMaxChunks; ++c) {
+            const int col = 4 * (gl + kG * c);
+            if (col < a.Ha) {
+                float t[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+                for (int db = 0; db < kFusedMaxPred / kPB; ++db) {
+                    if (db * kPB < a.pred_dim) {
+                        float4 w[kPB];
+#pragma unroll
+                        for (int e = 0; e < kPB; ++e) w[e] = *reinterpret_cast<const float4*>(s_wa + (db * kPB + e) * ldw + col);
+#pragma unroll
+                        for (int e = 0; e < kPB; ++e) {
+                            t[0] = fmaf(dp[db * kPB + e], w[e].x, t[0]); t[1] = fmaf(dp[db * kPB + e], w[e].y, t[1]);
+                            t[2] = fmaf(dp[db * kPB + e], w[e].z, t[2]); t[3] = fmaf(dp[db * kPB + e], w[e].w, t[3]);
+                        }
+                    }
+                }
+                const float y[4] = {ha[c].x, ha[c].y, ha[c].z, ha[c].w};
+                act_bwd4(t, y, a.act);
+                *reinterpret_cast<float4*>(dza + 4 * kG * c) = make_float4(t[0], t[1], t[2], t[3]);
+            }
+            if (col < a.Hc) {
+                const float4 w = *reinterpret_cast<const float4*>(s_wc + col);
+                float t[4] = {gv * w.x, gv * w.y, gv * w.z, gv * w.w};
+                const float y[4] = {hc[c].x, hc[c].y, hc[c].z, hc[c].w};
+                act_bwd4(t, y, a.act);
+                *reinterpret_cast<float4*>(dzc + 4 * kG * c) = make_float4(t[0], t[1], t[2], t[3]);
+            }
+        }
+        __syncwarp();                                                // s_pred / s_dpred are reused by the next sample
+#pragma unroll
+        for (int k = 0; k < kLossScalars; ++k) tot_sc[k] += double(sc[k]);
+#pragma unroll
+        for (int k = 0; k < kPerLane; ++k) tot_dsd[k] += double(dsd[k]);
+    }
+
+    // ---- CTA partials (fp64, fixed order) ----
+    if (lane == 0) {
+#pragma unroll
+        for (int k = 0; k < kLossScalars; ++k) s_red[warp][k] = tot_sc[k];
+    }
+#pragma unroll
+    for (int k = 0; k < kPerLane; ++k) s_red[warp][kLossScalars + lane + k * kG] = tot_dsd[k];
+    bar_stage();
+    const int n_vals = kLossScalars + (gaussian ? a.act_dim : 0);
+    double* part = reinterpret_cast<double*>(a.partials);
+    if (tid < n_vals) {
+        double t = 0.0;
+#pragma unroll
+        for (int w = 0; w < kStageThreads / 32; ++w) t += s_red[w][tid];
+        part[size_t(blockIdx.x) * kPartialStride + tid] = t;
+    }
+    bar_stage();
+}
+
+// Totals of the loss partials -> d(log_std) (+ its sum of squares) and the epoch statistics.  Run by the staging warps
+// of the last CTA at the start of the phase after LOSS (the partials are visible after the grid barrier).
+__device__ __forceinline__ void loss_finalize(const LossArgs& a, const float* s_dsd, double (*s_red)[kPartialStride],
+                                              double* s_tot, double* s_sq) {
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const bool gaussian = a.head == PPOAF_HEAD_GAUSSIAN_TANH;
+    const int n_vals = kLossScalars + (gaussian ? a.act_dim : 0);
+    const double* part = reinterpret_cast<const double*>(a.partials);
+    const float w_ent = float(a.hparams[PPOAF_HP_ENTROPY_WEIGHT]);
+    {
+        constexpr int kSub = kStageThreads / 32, kSlots = (kPartialStride + 31) / 32;
+        double acc3[kSlots];
+#pragma unroll
+        for (int q = 0; q < kSlots; ++q) acc3[q] = 0.0;
+        for (unsigned b = warp; b < gridDim.x; b += kSub) {
+#pragma unroll
+            for (int q = 0; q < kSlots; ++q) {
+                const int vi = lane + 32 * q;
+                if (vi < n_vals) acc3[q] += __ldcg(&part[size_t(b) * kPartialStride + vi]);
+            }
+        }
+#pragma unroll
+        for (int q = 0; q < kSlots; ++q) {
+            const int vi = lane + 32 * q;
+            if (vi < kPartialStride) s_red[warp][vi] = acc3[q];
+        }
+    }
+    bar_stage();
+    double my_sq = 0.0;
+    if (tid < n_vals) {
+        double t = 0.0;
+#pragma unroll
+        for (int w = 0; w < kStageThreads / 32; ++w) t += s_red[w][tid];
+        s_tot[tid] = t;
+        if (tid >= kLossScalars) {
+            const float gls = float(t) * s_dsd[tid - kLossScalars];
+            a.d_log_std[tid - kLossScalars] = gls;
+            for (int q = 0; q < a.n_mirror; ++q)
+                *reinterpret_cast<float*>(reinterpret_cast<char*>(a.d_log_std + (tid - kLossScalars)) + a.mirror_delta[q]) = gls;
+            my_sq = double(gls) * double(gls);
+        }
+    }
+    my_sq = warp_sum(my_sq);
+    if (lane == 0) s_sq[warp] = my_sq;
+    bar_stage();
+    if (tid == 0) {
+        if (a.sq_log_std) {
+            double t = 0.0;
+#pragma unroll
+            for (int k = 0; k < kStageThreads / 32; ++k) t += s_sq[k];
+            *a.sq_log_std = t;
+        }
+        const double nb = double(a.batch);
+        const float actor_mean = float(s_tot[LS_ACTOR] / nb);
+        const float critic_mean = float(s_tot[LS_CRITIC] / nb);
+        double* es = a.epoch_stats;
+        const double e0 = es[PPOAF_ST_ACTOR_LOSS], e1 = es[PPOAF_ST_CRITIC_LOSS], e2 = es[PPOAF_ST_ENTROPY], e3 = es[PPOAF_ST_KL];
+        const double e4 = es[PPOAF_ST_COUNTER], e5 = es[PPOAF_ST_BAD_RATIO], e6 = es[PPOAF_ST_BAD_VALUE];
+        es[PPOAF_ST_ACTOR_LOSS] = e0 + double(actor_mean);
+        es[PPOAF_ST_CRITIC_LOSS] = e1 + double(critic_mean);
+        if (w_ent != 0.f) es[PPOAF_ST_ENTROPY] = e2 + double(float(s_tot[LS_ENTROPY] / nb));
+        es[PPOAF_ST_KL] = e3 + double(float(s_tot[LS_KL] / nb));
+        es[PPOAF_ST_COUNTER] = e4 + 1.0;
+        es[PPOAF_ST_BAD_RATIO] = e5 + s_tot[LS_BAD_RATIO];
+        es[PPOAF_ST_BAD_VALUE] = e6 + s_tot[LS_BAD_VALUE];
+    }
+    bar_stage();
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// ADAM phase: arithmetic of adam_update_kernel (optim.cu) on this CTA's slice; t, beta^t are carried in registers /
+// shared memory across the steps of the launch.
+struct AdamC { float neg_step_size, bc2_sqrt, w1, beta2, w2, eps, inv_world; };
+__device__ __forceinline__ void adam_vec4(float4& pq, const float4& gq, float4& mq, float4& vq, float coef, const AdamC& c) {
+    float g[4] = {gq.x, gq.y, gq.z, gq.w}, p[4] = {pq.x, pq.y, pq.z, pq.w};
+    float mm[4] = {mq.x, mq.y, mq.z, mq.w}, vv[4] = {vq.x, vq.y, vq.z, vq.w};
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        const float gk = __fmul_rn(__fmul_rn(g[k], c.inv_world), coef);
+        mm[k] = __fadd_rn(mm[k], __fmul_rn(c.w1, __fsub_rn(gk, mm[k])));
+        vv[k] = __fadd_rn(__fmul_rn(vv[k], c.beta2), __fmul_rn(__fmul_rn(c.w2, gk), gk));
+        const float denom = __fadd_rn(__fdiv_rn(__fsqrt_rn(vv[k]), c.bc2_sqrt), c.eps);
+        p[k] = __fadd_rn(p[k], __fdiv_rn(__fmul_rn(c.neg_step_size, mm[k]), denom));
+    }
+    pq = make_float4(p[0], p[1], p[2], p[3]);
+    mq = make_float4(mm[0], mm[1], mm[2], mm[3]);
+    vq = make_float4(vv[0], vv[1], vv[2], vv[3]);
+}
+
+__device__ __forceinline__ void adam_phase(const FusedPlan& P, double p1, double p2, double* s_scr, float* s_f) {
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int64_t nv = P.n_total / 4, na = P.n_actor / 4;
+    const int64_t stride = int64_t(gridDim.x) * kStageThreads;
+    const int64_t i0 = int64_t(blockIdx.x) * kStageThreads + tid;
+    float4* p4 = reinterpret_cast<float4*>(P.params);
+    const float4* g4 = reinterpret_cast<const float4*>(P.grads);
+    float4* m4 = reinterpret_cast<float4*>(P.m);
+    float4* v4 = reinterpret_cast<float4*>(P.v);
+    constexpr int kSlots = 4;
+    float4 G[kSlots], Pq[kSlots], M[kSlots], V[kSlots];
+#pragma unroll
+    for (int k = 0; k < kSlots; ++k) {
+        const int64_t i = i0 + k * stride;
+        if (i < nv) { G[k] = __ldcg(g4 + i); Pq[k] = __ldcg(p4 + i); M[k] = __ldcg(m4 + i); V[k] = __ldcg(v4 + i); }
+    }
+    // fold the sum-of-squares slots (same order in every CTA -> identical scalars everywhere)
+    double ta = 0.0, tc = 0.0;
+    for (int k = tid; k < P.n_sq_a; k += kStageThreads) ta += __ldcg(P.sq_a + k);
+    for (int k = tid; k < P.n_sq_c; k += kStageThreads) tc += __ldcg(P.sq_c + k);
+    ta = warp_sum(ta);
+    tc = warp_sum(tc);
+    if (lane == 0) { s_scr[warp] = ta; s_scr[8 + warp] = tc; }
+    bar_stage();
+    if (tid == 0) {
+        double sa = 0.0, sc = 0.0;
+#pragma unroll
+        for (int k = 0; k < kStageThreads / 32; ++k) { sa += s_scr[k]; sc += s_scr[8 + k]; }
+        const double* hp = P.hp;
+        const float inv_world = float(hp[PPOAF_HP_INV_WORLD]);
+        const float max_norm = float(hp[PPOAF_HP_GRAD_CLIP]);
+        const double scale = double(inv_world);
+        float ca = 1.f, cc = 1.f;
+        if (max_norm >= 0.f) {
+            ca = fminf(max_norm / (float(sqrt(sa) * scale) + 1e-6f), 1.f);
+            cc = fminf(max_norm / (float(sqrt(sc) * scale) + 1e-6f), 1.f);
+        }
+        const double b1d = hp[PPOAF_HP_BETA1], b2d = hp[PPOAF_HP_BETA2];
+        const double bc1 = 1.0 - p1, bc2 = 1.0 - p2;
+        s_f[0] = float(-(hp[PPOAF_HP_LR] / bc1));
+        s_f[1] = float(sqrt(bc2));
+        s_f[2] = float(1.0 - b1d);
+        s_f[3] = float(b2d);
+        s_f[4] = float(1.0 - b2d);
+        s_f[5] = float(hp[PPOAF_HP_ADAM_EPS]);
+        s_f[6] = inv_world;
+        s_f[7] = ca;
+        s_f[8] = cc;
+    }
+    bar_stage();
+    const AdamC c{s_f[0], s_f[1], s_f[2], s_f[3], s_f[4], s_f[5], s_f[6]};
+    const float coef_a = s_f[7], coef_c = s_f[8];
+#pragma unroll
+    for (int k = 0; k < kSlots; ++k) {
+        const int64_t i = i0 + k * stride;
+        if (i < nv) {
+            adam_vec4(Pq[k], G[k], M[k], V[k], i < na ? coef_a : coef_c, c);
+            p4[i] = Pq[k]; m4[i] = M[k]; v4[i] = V[k];
+        }
+    }
+    for (int64_t i = i0 + kSlots * stride; i < nv; i += stride) {
+        const float4 gq = __ldcg(g4 + i);
+        float4 pq = __ldcg(p4 + i), mq = __ldcg(m4 + i), vq = __ldcg(v4 + i);
+        adam_vec4(pq, gq, mq, vq, i < na ? coef_a : coef_c, c);
+        p4[i] = pq; m4[i] = mq; v4[i] = vq;
+    }
+    bar_stage();                                                    // s_scr / s_f are reused by the next step
+}
+
+__global__ void __launch_bounds__(kFThreads, 1) ppo_fused_step_kernel(const __grid_constant__ FusedPlan P) {
+    extern __shared__ uint8_t smem_raw[];
+    __shared__ __align__(8) uint64_t s_bars[2 * kFStages + 1];
+    __shared__ uint32_t s_tmem;
+    __shared__ float s_sd[kMaxAct], s_dsd[kMaxAct];
+    __shared__ double s_red[kStageThreads / 32][kPartialStride];
+    __shared__ double s_tot[kPartialStride];
+    __shared__ double s_sq[kStageThreads / 32];
+    __shared__ double s_scr[16];
+    __shared__ float s_f[12];
+    float* smem = reinterpret_cast<float*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    const int tid = threadIdx.x, warp = tid >> 5;
+
+    if (warp == 0) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&s_tmem)), "r"(kFTmemCols));
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+    }
+    if (tid == 32) {
+#pragma unroll
+        for (int i = 0; i < kFStages; ++i) {
+            mbar_init(&s_bars[i], kStageThreads / 32);
+            mbar_init(&s_bars[kFStages + i], 1);
+        }
+        mbar_init(&s_bars[2 * kFStages], 1);
+        asm volatile("fence.mbarrier_init.release.cluster;");
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    const uint32_t tmem = s_tmem;
+
+    // launch-wide state, read before the first grid barrier (the counters are only written at the very end)
+    uint32_t epoch = P.bar[kMaxGrid * kBarStride];
+    const int cur0 = *P.mb_cursor;
+    const int64_t t0 = *P.adam_step;
+
+    if (warp >= kStageThreads / 32) {
+        // ============================ MMA warpgroup: warp 8 / lane 0 issues, the rest only keeps the barriers company ============================
+        asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(kMmaRegs));
+        uint32_t gchunk = 0;
+        const bool issuer = warp == kStageThreads / 32 && (tid & 31) == 0;
+        for (int step = 0; step < P.n_steps; ++step) {
+            for (int ph = 0; ph < P.n_phases; ++ph) {
+                if (step > 0 || ph > 0) grid_sync(P.bar, ++epoch);
+                const PhaseDesc d = P.ph[ph];
+                if (d.type == PH_LOSS || d.type == PH_ADAM || !issuer) continue;
+                for (int t = int(blockIdx.x); t < d.n_tiles; t += int(gridDim.x)) {
+                    int pi = d.first;
+                    for (int i = d.first + 1; i < d.first + d.count; ++i)
+                        if (t >= P.p[i].tile_begin) pi = i;
+                    ftile_mma(P.p[pi], d.type != PH_BWD_W, d.type == PH_FWD, smem, s_bars, tmem, gchunk);
+                }
+            }
+        }
+    } else {
+        // ============================ staging / epilogue / loss / optimizer warps ============================
+        asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(kStageRegs));
+        double p1 = 0.0, p2 = 0.0;
+        const double b1d = P.hp[PPOAF_HP_BETA1], b2d = P.hp[PPOAF_HP_BETA2];
+        if (tid == 0) { p1 = pow(b1d, double(t0)); p2 = pow(b2d, double(t0)); }
+        uint32_t gchunk = 0, gtile = 0;
+        for (int step = 0; step < P.n_steps; ++step) {
+            const int cur = cur0 + step;
+            const int64_t idx_off = int64_t(cur) * P.batch_size;
+            p1 *= b1d; p2 *= b2d;                                     // beta^t of this step (thread 0)
+            for (int ph = 0; ph < P.n_phases; ++ph) {
+                if (step > 0 || ph > 0) grid_sync(P.bar, ++epoch);
+                const PhaseDesc d = P.ph[ph];
+                if (ph == P.loss_finalize_phase && blockIdx.x == gridDim.x - 1) loss_finalize(P.loss, s_dsd, s_red, s_tot, s_sq);
+                if (d.type == PH_LOSS) {
+                    loss_phase(P.loss, cur, smem, s_sd, s_dsd, s_red);
+                } else if (d.type == PH_ADAM) {
+                    adam_phase(P, p1, p2, s_scr, s_f);
+                } else {
+                    for (int t = int(blockIdx.x); t < d.n_tiles; t += int(gridDim.x)) {
+                        int pi = d.first;
+                        for (int i = d.first + 1; i < d.first + d.count; ++i)
+                            if (t >= P.p[i].tile_begin) pi = i;
+                        const GemmProblem& g = P.p[pi];
+                        const int tile = t - g.tile_begin;
+                        if (d.type == PH_FWD) ftile<true, true, EPI_FWD>(g, tile, idx_off, P.mirror, smem, s_bars, tmem, gchunk, gtile, s_sq);
+                        else if (d.type == PH_BWD_X) ftile<true, false, EPI_BWD_X>(g, tile, idx_off, P.mirror, smem, s_bars, tmem, gchunk, gtile, s_sq);
+                        else ftile<false, false, EPI_BWD_W>(g, tile, idx_off, P.mirror, smem, s_bars, tmem, gchunk, gtile, s_sq);
+                    }
+                }
+            }
+        }
+        // counters of the launch: every CTA read them before its first grid barrier
+        if (blockIdx.x == 0 && tid == 0) {
+            *P.adam_step = t0 + P.n_steps;
+            *P.mb_cursor = cur0 + P.n_steps;
+            P.bar[kMaxGrid * kBarStride] = epoch;
+        }
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(kFTmemCols));
+}
+
+}  // namespace fused
+}  // namespace ppoaf
+
+// =========================================================================================================
+// host side: workspace layout, plan construction, entry points
+// =========================================================================================================
+namespace ppoaf {
+namespace fused {
+
+struct FScratch {
+    uint32_t* bar;
+    double* sq_actor; double* sq_critic;
+    int n_sq_actor, n_sq_critic;
+    double* loss_partials;
+    float* act[2][PPOAF_MAX_LAYERS + 1];
+    float* dz[2][PPOAF_MAX_LAYERS + 1];
+    size_t total;
+};
+
+static inline int ceil_div(int a, int b) { return (a + b - 1) / b; }
+static int max_w_tiles(const ppoaf_mlp_desc* net) {      // upper bound of the backward-w tiles of one network (bn = 32)
+    int n = 0;
+    for (int l = 0; l < net->n_layers; ++l) n += ceil_div(net->dims[l + 1], kFM) * ceil_div(net->dims[l], 32);
+    return n;
+}
+
+static void fcarve(const ppoaf_update_cfg* cfg, int max_batch, char* base, FScratch* out) {
+    size_t off = 0;
+    auto take = [&](size_t bytes) {
+        char* p = base ? base + off : nullptr;
+        off += align_up(bytes, 256);
+        return p;
+    };
+    // control words first, at offsets that do not depend on the batch: they persist from launch to launch
+    out->bar = reinterpret_cast<uint32_t*>(take(sizeof(uint32_t) * (size_t(kMaxGrid) * kBarStride + 8)));
+    out->n_sq_actor = max_w_tiles(&cfg->actor) + 1;
+    out->n_sq_critic = max_w_tiles(&cfg->critic);
+    out->sq_actor = reinterpret_cast<double*>(take(size_t(out->n_sq_actor) * sizeof(double)));
+    out->sq_critic = reinterpret_cast<double*>(take(size_t(out->n_sq_critic) * sizeof(double)));
+    out->loss_partials = reinterpret_cast<double*>(take(size_t(kMaxGrid) * kPartialStride * sizeof(double)));
+    const ppoaf_mlp_desc* nets[2] = {&cfg->actor, &cfg->critic};
+    for (int k = 0; k < 2; ++k)
+        for (int l = 1; l <= nets[k]->n_layers; ++l) {
+            out->act[k][l] = reinterpret_cast<float*>(take(size_t(max_batch) * nets[k]->dims[l] * sizeof(float)));
+            out->dz[k][l] = reinterpret_cast<float*>(take(size_t(max_batch) * nets[k]->dims[l] * sizeof(float)));
+        }
+    out->total = off;
+}
+
+static const char* unsupported_reason(const ppoaf_update_cfg* cfg) {
+    const int La = cfg->actor.n_layers, Lc = cfg->critic.n_layers;
+    if (La != Lc) return "actor and critic depths differ";
+    if (La < 2) return "networks without a hidden layer";
+    if (cfg->actor.activation != cfg->critic.activation) return "actor and critic activations differ";
+    if (!loss_head_fusable(cfg->actor.dims[La], cfg->actor.dims[La - 1], cfg->critic.dims[Lc - 1], cfg->vf_clip_enabled))
+        return "head layers are not fusable (hidden width > 256 or not a multiple of 4, > 24 actor outputs, or value clipping)";
+    if (cfg->act_dim > kMaxAct || cfg->actor.dims[La] > kMaxAct) return "action width out of range";
+    if (cfg->world_size > 1) return "multi-rank exchange runs through the launch-chain path";
+    return nullptr;
+}
+
+static inline bool vec4_ok(const float* p, int ld, int contig_extent) {
+    return (reinterpret_cast<uintptr_t>(p) % 16 == 0) && (ld % 4 == 0) && (contig_extent % 4 == 0);
+}
+
+// tile width of a phase: the widest bn whose tile count reaches ~2/3 of the grid, else the narrowest allowed
+static int pick_bn(int grid, int min_bn, const int (*MN)[2], int n_prob) {
+    const int cand[3] = {64, 32, 16};
+    for (int c = 0; c < 3; ++c) {
+        const int bn = cand[c];
+        if (bn < min_bn) break;
+        int tiles = 0;
+        for (int i = 0; i < n_prob; ++i) tiles += ceil_div(MN[i][0], kFM) * ceil_div(MN[i][1], bn);
+        if (tiles * 3 >= grid * 2 || bn == min_bn) return bn;
+    }
+    return min_bn;
+}
+
+static int build_plan(const ppoaf_update_cfg* cfg, const ppoaf_update_bufs* b, int n_steps, int grid, FusedPlan* P) {
+    memset(P, 0, sizeof(*P));
+    FScratch sc;
+    fcarve(cfg, b->batch_size, reinterpret_cast<char*>(b->workspace), &sc);
+    const bool gaussian = cfg->head == PPOAF_HEAD_GAUSSIAN_TANH;
+    int64_t off[2][2 * PPOAF_MAX_LAYERS + 1];
+    const int64_t n_actor = param_layout(&cfg->actor, gaussian ? cfg->act_dim : 0, off[0]);
+    const int64_t n_critic = param_layout(&cfg->critic, 0, off[1]);
+    const ppoaf_mlp_desc* net[2] = {&cfg->actor, &cfg->critic};
+    const float* par[2] = {b->params, b->params + n_actor};
+    float* grd[2] = {b->grads, b->grads + n_actor};
+    const float* x0[2] = {b->obs, b->critic_obs};
+    const int L = cfg->actor.n_layers;
+    const int rows = b->batch;
+
+    P->n_steps = n_steps;
+    P->batch = rows;
+    P->batch_size = b->batch_size;
+    int np = 0, nph = 0;
+    auto begin_phase = [&](int type) { P->ph[nph].type = type; P->ph[nph].first = np; P->ph[nph].count = 0; P->ph[nph].n_tiles = 0; };
+    auto add_problem = [&](GemmProblem& g, int bn) {
+        g.bn = bn;
+        g.tiles_n = ceil_div(g.N, bn);
+        g.tile_begin = P->ph[nph].n_tiles;
+        P->ph[nph].n_tiles += g.tiles_n * ceil_div(g.M, kFM);
+        P->ph[nph].count += 1;
+        P->p[np++] = g;
+    };
+
+    // ---- forward, hidden layers ----
+    for (int l = 0; l < L - 1; ++l) {
+        begin_phase(PH_FWD);
+        const int MN[2][2] = {{rows, net[0]->dims[l + 1]}, {rows, net[1]->dims[l + 1]}};
+        const int bn = pick_bn(grid, 16, MN, 2);
+        for (int k = 0; k < 2; ++k) {
+            GemmProblem g{};
+            const float* X = l == 0 ? x0[k] : sc.act[k][l];
+            const int in = net[k]->dims[l], out = net[k]->dims[l + 1];
+            const float* W = par[k] + off[k][2 * l];
+            g.A = X; g.lda = in; g.B = W; g.ldb = in; g.C = sc.act[k][l + 1]; g.ldc = out;
+            g.M = rows; g.N = out; g.K = in;
+            g.idxA = l == 0 ? b->perm : nullptr;
+            g.bias = par[k] + off[k][2 * l + 1];
+            g.act = net[k]->activation;
+            g.flavour = EPI_FWD * 4 + (vec4_ok(X, in, in) ? 2 : 0) + (vec4_ok(W, in, in) ? 1 : 0);
+            add_problem(g, bn);
+        }
+        ++nph;
+    }
+    // ---- heads + loss ----
+    begin_phase(PH_LOSS);
+    ++nph;
+    P->loss_finalize_phase = nph;
+    // ---- backward-x, top hidden layer first ----
+    for (int l = L - 2; l >= 1; --l) {
+        begin_phase(PH_BWD_X);
+        const int MN[2][2] = {{rows, net[0]->dims[l]}, {rows, net[1]->dims[l]}};
+        const int bn = pick_bn(grid, 32, MN, 2);          // MN-major B tiles: groups of 32 outputs
+        for (int k = 0; k < 2; ++k) {
+            GemmProblem g{};
+            const int in = net[k]->dims[l], out = net[k]->dims[l + 1];
+            const float* W = par[k] + off[k][2 * l];
+            g.A = sc.dz[k][l + 1]; g.lda = out; g.B = W; g.ldb = in; g.C = sc.dz[k][l]; g.ldc = in;
+            g.M = rows; g.N = in; g.K = out;
+            g.aux = sc.act[k][l]; g.ldaux = in; g.act = net[k]->activation;
+            g.flavour = EPI_BWD_X * 4 + (vec4_ok(g.A, out, out) ? 2 : 0) + (vec4_ok(W, in, in) ? 1 : 0);
+            add_problem(g, bn);
+        }
+        ++nph;
+    }
+    // ---- backward-w, every layer of both networks in one phase ----
+    {
+        begin_phase(PH_BWD_W);
+        int MN[2 * PPOAF_MAX_LAYERS][2];
+        int cnt = 0;
+        for (int k = 0; k < 2; ++k)
+            for (int l = 0; l < L; ++l) { MN[cnt][0] = net[k]->dims[l + 1]; MN[cnt][1] = net[k]->dims[l]; ++cnt; }
+        const int bn = pick_bn(grid, 32, MN, cnt);
+        double* sq[2] = {sc.sq_actor, sc.sq_critic};
+        int used[2] = {0, 0};
+        for (int k = 0; k < 2; ++k)
+            for (int l = L - 1; l >= 0; --l) {             // widest-K problems (none here: K = rows for all) / top layers first
+                GemmProblem g{};
+                const int in = net[k]->dims[l], out = net[k]->dims[l + 1];
+                const float* X = l == 0 ? x0[k] : sc.act[k][l];
+                g.A = sc.dz[k][l + 1]; g.lda = out; g.B = X; g.ldb = in; g.C = grd[k] + off[k][2 * l]; g.ldc = in;
+                g.M = out; g.N = in; g.K = rows;
+                g.idxB = l == 0 ? b->perm : nullptr;
+                g.dbias = grd[k] + off[k][2 * l + 1];
+                g.sq_out = sq[k] + used[k];
+                g.flavour = EPI_BWD_W * 4 + (vec4_ok(g.A, out, out) ? 2 : 0) + (vec4_ok(X, in, in) ? 1 : 0);
+                used[k] += ceil_div(out, kFM) * ceil_div(in, bn);
+                add_problem(g, bn);
+            }
+        P->sq_a = sc.sq_actor; P->n_sq_a = used[0] + 1;     // + the log_std slot (zero for the Categorical head)
+        P->sq_c = sc.sq_critic; P->n_sq_c = used[1];
+        ++nph;
+    }
+    begin_phase(PH_ADAM);
+    ++nph;
+    P->n_phases = nph;
+    P->n_problems = np;
+
+    // ---- loss arguments (fused heads) ----
+    LossArgs& a = P->loss;
+    a.log_std = gaussian ? par[0] + off[0][2 * L] : nullptr;
+    a.raw_actions = b->raw_actions;
+    a.advantages = b->advantages;
+    a.log_probs = b->log_probs;
+    a.rewards_to_go = b->rewards_to_go;
+    a.values = b->values;
+    a.perm = b->perm;
+    a.cursor = b->mb_cursor;
+    a.batch_size = b->batch_size;
+    a.batch = rows;
+    a.mb_adv_stats = b->mb_adv_stats;
+    a.mb_val_stats = b->mb_val_stats;
+    a.hparams = b->hparams;
+    a.epoch_stats = b->epoch_stats;
+    a.d_actor_out = sc.dz[0][L];
+    a.d_critic_out = sc.dz[1][L];
+    a.d_log_std = gaussian ? grd[0] + off[0][2 * L] : nullptr;
+    a.sq_log_std = sc.sq_actor + (P->n_sq_a - 1);
+    a.partials = reinterpret_cast<float*>(sc.loss_partials);
+    a.head = cfg->head;
+    a.act_dim = cfg->act_dim;
+    a.pred_dim = cfg->actor.dims[L];
+    a.use_huber = cfg->use_huber;
+    a.normalize_adv = cfg->normalize_adv;
+    a.normalize_values = cfg->normalize_values;
+    a.vf_clip_enabled = 0;
+    a.min_std = cfg->min_std;
+    a.pf_rows[0] = b->obs;
+    a.pf_rows[1] = b->critic_obs;
+    a.pf_row_bytes[0] = cfg->actor.dims[0] * int(sizeof(float));
+    a.pf_row_bytes[1] = cfg->critic.dims[0] * int(sizeof(float));
+    a.n_flat = b->n_flat;
+    a.n_mirror = 0;
+    a.fused = 1;
+    a.h_actor = sc.act[0][L - 1];
+    a.h_critic = sc.act[1][L - 1];
+    a.W_actor = par[0] + off[0][2 * (L - 1)];
+    a.b_actor = par[0] + off[0][2 * (L - 1) + 1];
+    a.W_critic = par[1] + off[1][2 * (L - 1)];
+    a.b_critic = par[1] + off[1][2 * (L - 1) + 1];
+    a.dz_actor = sc.dz[0][L - 1];
+    a.dz_critic = sc.dz[1][L - 1];
+    a.Ha = cfg->actor.dims[L - 1];
+    a.Hc = cfg->critic.dims[L - 1];
+    a.act = cfg->actor.activation;
+
+    P->mirror.n = 0;
+    P->params = b->params; P->grads = b->grads; P->m = b->adam_m; P->v = b->adam_v;
+    P->n_actor = n_actor; P->n_total = n_actor + n_critic;
+    P->hp = b->hparams;
+    P->adam_step = b->adam_step;
+    P->mb_cursor = b->mb_cursor;
+    P->bar = sc.bar;
+    return 0;
+}
+
+static bool g_fused_configured = false;
+static void configure_fused() {
+    g_fused_configured = true;
+    cudaFuncSetAttribute(ppo_fused_step_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, int(kFusedSmemBytes));
+}
+
+}  // namespace fused
+}  // namespace ppoaf
+
+using namespace ppoaf;
+
+extern "C" int ppoaf_ppo_fused_supported(const ppoaf_update_cfg* cfg) {
+    if (!cfg) return 0;
+    if (check_mlp_desc(&cfg->actor, "ppoaf_ppo_fused_supported") || check_mlp_desc(&cfg->critic, "ppoaf_ppo_fused_supported")) return 0;
+    const char* why = fused::unsupported_reason(cfg);
+    if (why) { set_error("ppoaf_ppo_fused_steps: not supported: %s", why); return 0; }
+    return 1;
+}
+
+extern "C" size_t ppoaf_ppo_fused_workspace_bytes(const ppoaf_update_cfg* cfg, int32_t max_batch) {
+    if (!cfg || max_batch <= 0) return 0;
+    fused::FScratch s;
+    fused::fcarve(cfg, max_batch, nullptr, &s);
+    return s.total;
+}
+
+extern "C" int ppoaf_ppo_fused_steps(const ppoaf_update_cfg* cfg, const ppoaf_update_bufs* b, int32_t n_steps, void* stream) {
+    PPOAF_CHECK_ARG(cfg != nullptr && b != nullptr, "ppoaf_ppo_fused_steps: null argument");
+    if (check_mlp_desc(&cfg->actor, "ppoaf_ppo_fused_steps") || check_mlp_desc(&cfg->critic, "ppoaf_ppo_fused_steps")) return 1;
+    const char* why = fused::unsupported_reason(cfg);
+    PPOAF_CHECK_ARG(why == nullptr, "ppoaf_ppo_fused_steps: not supported: %s", why ? why : "");
+    PPOAF_CHECK_ARG(cfg->critic.dims[cfg->critic.n_layers] == 1, "ppoaf_ppo_fused_steps: critic output width must be 1");
+    PPOAF_CHECK_ARG(b->batch >= 2 && b->batch <= b->batch_size && b->n_flat > 0 && n_steps >= 1,
+                    "ppoaf_ppo_fused_steps: bad batch sizes (one-row minibatches are skipped by the caller)");
+    PPOAF_CHECK_ARG(n_steps == 1 || b->batch == b->batch_size, "ppoaf_ppo_fused_steps: several steps need full minibatches");
+    PPOAF_CHECK_ARG(b->workspace_bytes >= ppoaf_ppo_fused_workspace_bytes(cfg, b->batch_size),
+                    "ppoaf_ppo_fused_steps: workspace too small");
+    PPOAF_CHECK_ARG(reinterpret_cast<uintptr_t>(b->workspace) % 256 == 0, "ppoaf_ppo_fused_steps: workspace must be 256-byte aligned");
+    PPOAF_CHECK_ARG((cfg->actor.n_layers * 6) <= fused::kMaxProblems, "ppoaf_ppo_fused_steps: too many layers");
+    if (!fused::g_fused_configured) fused::configure_fused();
+    int grid = sm_count();
+    if (grid > fused::kMaxGrid) grid = fused::kMaxGrid;
+    static thread_local fused::FusedPlan plan;
+    if (fused::build_plan(cfg, b, n_steps, grid, &plan)) return 1;
+
+    cudaLaunchConfig_t lc = {};
+    lc.gridDim = dim3(grid); lc.blockDim = dim3(fused::kFThreads); lc.dynamicSmemBytes = fused::kFusedSmemBytes;
+    lc.stream = (cudaStream_t)stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeCooperative;      // all CTAs co-resident: the phases are separated by grid barriers
+    attr[0].val.cooperative = 1;
+    lc.attrs = attr; lc.numAttrs = 1;
+    cudaError_t e = cudaLaunchKernelEx(&lc, fused::ppo_fused_step_kernel, plan);
+    if (e != cudaSuccess) {
+        set_error("ppo_fused_step_kernel: launch failed: %s", cudaGetErrorString(e));
+        return 2;
+    }
+    return 0;
+}

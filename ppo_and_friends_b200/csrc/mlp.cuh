@@ -65,6 +65,7 @@ struct GemmProblem {
     int tile_begin;                 // first linear tile id of this problem inside the launch
     int b_static;                   // B is not written by the launch right before this one (and has no gather): it may
                                     //   be staged before the programmatic-dependency wait
+    int bn;                         // fused_step.cu: tile width along N chosen for this problem's phase (16 / 32 / 64)
 };
 struct MirrorSet {                   // peer copies of the gradient buffer (R > 1 push exchange): byte offsets from
     int n;                           //   a local gradient address to the same element in every peer's receive slot
@@ -442,6 +443,7 @@ __device__ __forceinline__ void gemm_tile(const GemmProblem& g, int tile, const 
     }
 }
 
+#ifndef PPOAF_HELPERS_ONLY   // fused_step.cu reuses the helpers above; the kernel itself lives in mlp.cu's translation unit
 __global__ void __launch_bounds__(kThreads) grouped_gemm_kernel(const GroupedGemmArgs args) {
     extern __shared__ __align__(16) float smem[];
     __shared__ __align__(8) uint64_t s_bars[kLoadGroups];
@@ -484,5 +486,6 @@ __global__ void __launch_bounds__(kThreads) grouped_gemm_kernel(const GroupedGem
 #endif
 #undef PPOAF_TILE
 }
+#endif  // PPOAF_HELPERS_ONLY
 
 }  // namespace ppoaf

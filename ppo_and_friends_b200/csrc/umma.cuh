@@ -162,6 +162,7 @@ __device__ __forceinline__ uint64_t desc_base() {
 template <bool RC>
 __device__ __forceinline__ uint32_t kstep_units() { return RC ? 2u : 64u; }   // 16-byte units per k-step
 
+#ifndef PPOAF_HELPERS_ONLY
 // Warp roles: warps 0..7 stage operands and run the epilogue; warp 8 (one lane) issues the MMAs.
 //   full[s]  : 8 arrivals (one per staging warp, after its stores + proxy fence)  -> MMA warp may read stage s
 //   free[s]  : tcgen05.commit                                                     -> stage s may be overwritten
@@ -393,6 +394,8 @@ __global__ void __launch_bounds__(kUThreads + 32) umma_grouped_gemm_kernel(const
     __syncthreads();
     if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(kTmemCols));
 }
+
+#endif  // PPOAF_HELPERS_ONLY
 
 }  // namespace umma
 }  // namespace ppoaf

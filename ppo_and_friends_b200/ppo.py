@@ -81,6 +81,14 @@ class UpdateEngine:
         self.mb_cursor = torch.zeros(1, dtype=torch.int32, device=dev)
         ws_bytes = load().ppoaf_update_workspace_bytes(C.byref(cfg), self.batch_size)
         self.workspace = torch.zeros(ws_bytes + 256, dtype=torch.uint8, device=dev)
+        # The whole-epoch persistent kernel (csrc/fused_step.cu) is the default step engine wherever it applies
+        # (PPOAF_STEP=chain selects the launch-chain path: one CUDA graph of 8 launches per minibatch)
+        self.fused = (os.environ.get("PPOAF_STEP", "fused") != "chain" and self.peer is None and cfg.world_size == 1
+                      and bool(load().ppoaf_ppo_fused_supported(C.byref(cfg))))
+        self.fused_workspace = None
+        if self.fused:
+            fbytes = load().ppoaf_ppo_fused_workspace_bytes(C.byref(cfg), self.batch_size)
+            self.fused_workspace = torch.zeros(fbytes + 256, dtype=torch.uint8, device=dev)   # barrier words start at zero
         self.null_state = torch.tensor([0.0, 1.0, 1e-4], dtype=torch.float64, device=dev)
         self._graphs = {}
         self._spec_perm = None          # (n, rng state before, rng state after, permutation) drawn ahead of time
@@ -102,7 +110,7 @@ class UpdateEngine:
         self.hparams.copy_(h, non_blocking=True)
 
     # -- buffers struct for a given dataset / minibatch size ---------------------------------------------
-    def _bufs(self, ds, rows, parity=0):
+    def _bufs(self, ds, rows, parity=0, fused=False):
         nets = self.policy.nets
         b = _lib.UpdateBufs()
         b.critic_obs, b.obs = ds.critic_observations.data_ptr(), ds.observations.data_ptr()
@@ -116,9 +124,10 @@ class UpdateEngine:
         b.adam_m, b.adam_v, b.adam_step = nets.adam_m.data_ptr(), nets.adam_v.data_ptr(), nets.adam_step.data_ptr()
         b.hparams, b.epoch_stats = self.hparams.data_ptr(), self.epoch_stats.data_ptr()
         b.mb_cursor = self.mb_cursor.data_ptr()
-        ws = self.workspace.data_ptr()
+        wst = self.fused_workspace if fused else self.workspace
+        ws = wst.data_ptr()
         b.workspace = (ws + 255) // 256 * 256
-        b.workspace_bytes = self.workspace.numel() - 256
+        b.workspace_bytes = wst.numel() - 256
         b.n_flat = len(ds)
         b.batch, b.batch_size = int(rows), self.batch_size
         if self.peer is not None:                              # push exchange: mirror every gradient store into the peers
@@ -134,6 +143,12 @@ class UpdateEngine:
     def _apply(self, bufs):
         check(load().ppoaf_ppo_minibatch_apply(C.byref(self.cfg), C.byref(bufs), stream_ptr()),
               "ppoaf_ppo_minibatch_apply")
+
+    def _fused_steps(self, ds, rows, n_steps):
+        """n_steps consecutive minibatches of `rows` rows in ONE persistent launch (no graph needed: one launch per epoch)."""
+        bufs = self._bufs(ds, rows, fused=True)
+        check(load().ppoaf_ppo_fused_steps(C.byref(self.cfg), C.byref(bufs), int(n_steps), stream_ptr()),
+              "ppoaf_ppo_fused_steps")
 
     def _step_eager(self, bufs, parity=0):
         self._grads(bufs)
@@ -262,7 +277,15 @@ class UpdateEngine:
         n_full = n // self.batch_size
         # PPOAF_EPOCH_GRAPH=0 falls back to one graph replay per minibatch
         eg = os.environ.get("PPOAF_EPOCH_GRAPH", "1")
-        if (self.use_graphs and n_full >= 2 and eg == "1"
+        if self.fused:
+            rem = n - n_full * self.batch_size
+            if n_full >= 1:
+                self._fused_steps(ds, self.batch_size, n_full)
+            if rem >= 2:
+                self._fused_steps(ds, rem, 1)
+            elif rem == 1:                                     # the reference skips one-row minibatches: the cursor moves on
+                self._apply(self._bufs(ds, 1))
+        elif (self.use_graphs and n_full >= 2 and eg == "1"
                 and (mpi_utils.get_num_procs() == 1 or self.peer is not None)):
             self._launch_full_minibatches(ds, n_full)          # ONE graph for all full minibatches of the epoch
             if n - n_full * self.batch_size > 0:

@@ -20,10 +20,16 @@ SEG_CASES = ["seg_single", "seg_multi", "seg_bsclip", "seg_nogae", "seg_dynclip"
              "seg_len1", "seg_open", "seg_max1"]          # edge shapes: all length-1, never-ending, cut at every step
 
 
-@pytest.fixture(params=["ffma", "tcgen05"])
-def gemm_backend(request):
-    """Run a test on both engines of the MLP GEMM phases (FFMA tiles; tcgen05 3xTF32 tensor-core tiles)."""
+@pytest.fixture(params=["fused", "ffma", "tcgen05"])
+def gemm_backend(request, monkeypatch):
+    """Run a test on every engine of the minibatch step: the persistent whole-epoch kernel (tcgen05 3xTF32 tiles, the
+    default) and the launch-chain path with FFMA tiles or tcgen05 tiles."""
     from ppo_and_friends_b200 import ops
+    if request.param == "fused":
+        monkeypatch.setenv("PPOAF_STEP", "fused")
+        yield request.param
+        return
+    monkeypatch.setenv("PPOAF_STEP", "chain")
     ops.set_gemm_backend(request.param)
     yield request.param
     ops.set_gemm_backend("ffma")
