@@ -8,6 +8,7 @@ namespace ppoaf {
 enum { GEMM_BACKEND_FFMA = 0, GEMM_BACKEND_TCGEN05 = 1 };
 int gemm_backend();             // PPOAF_GEMM=ffma|tcgen05 (default tcgen05: 3xTF32 tensor-core tiles)
 struct GroupedGemmArgs;
+constexpr int kMaxGroupHost = 16;   // problems one grouped launch carries (== kMaxGroup of mlp.cuh)
 struct GemmGroup {
     GroupedGemmArgs* args;      // owned
     int n_tiles;
@@ -16,6 +17,7 @@ struct GemmGroup {
     ~GemmGroup();
     GemmGroup(const GemmGroup&) = delete;
     GemmGroup& operator=(const GemmGroup&) = delete;
+    void reset();               // empty the group for reuse after launch()
     // Y[rows, out] = act(X[idx][rows, in] W^T + b)
     // w_static / x_static: the operand is not written by the launch that precedes this one in the stream, so the
     // FFMA kernel may stage it before its programmatic-dependency wait (see common.cuh, PDL)

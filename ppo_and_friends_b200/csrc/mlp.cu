@@ -25,6 +25,8 @@ static inline int tile_n(int backend) { return backend == GEMM_BACKEND_TCGEN05 ?
 
 GemmGroup::GemmGroup(int backend_) : args(new GroupedGemmArgs()), n_tiles(0), backend(backend_) { args->n_problems = 0; }
 GemmGroup::~GemmGroup() { delete args; }
+void GemmGroup::reset() { args->n_problems = 0; n_tiles = 0; }
+static_assert(kMaxGroupHost == kMaxGroup, "internal.h and mlp.cuh disagree on the group size");
 
 static GemmProblem* next_problem(GemmGroup* grp, int M, int N) {
     GemmProblem* g = &grp->args->p[grp->args->n_problems++];

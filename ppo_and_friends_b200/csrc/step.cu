@@ -64,7 +64,7 @@ struct StepScratch {
 
 static int count_sq_slots(const ppoaf_mlp_desc* net) {
     int n = 0;
-    for (int l = 0; l < net->n_layers; ++l) n += backward_w_tiles(net->dims[l], net->dims[l + 1], gemm_backend());
+    for (int l = 0; l < net->n_layers; ++l) n += backward_w_tiles(net->dims[l], net->dims[l + 1], GEMM_BACKEND_FFMA);
     return n;
 }
 
@@ -206,7 +206,7 @@ extern "C" int ppoaf_ppo_minibatch_grads(const ppoaf_update_cfg* cfg, const ppoa
 
     // ---- forward: layer l of both networks in one grouped launch ----
     for (int l = 0; l < Lmax - (fuse_heads ? 1 : 0); ++l) {
-        GemmGroup grp(gemm_backend());
+        GemmGroup grp(GEMM_BACKEND_FFMA);   // the update always runs the FFMA tiles: fp32 FMA accuracy (the stand-alone tcgen05 tiles keep one accumulator)
         for (int k = 0; k < 2; ++k) {
             if (l >= L[k]) continue;
             const bool first = l == 0, last = l + 1 == L[k];
@@ -279,7 +279,7 @@ extern "C" int ppoaf_ppo_minibatch_grads(const ppoaf_update_cfg* cfg, const ppoa
     double* sq[2] = {sc.sq_actor, sc.sq_critic};
     int sq_used[2] = {0, 0};
     for (int k_top = fuse_heads ? 1 : 0; k_top < Lmax; ++k_top) {
-        GemmGroup grp(gemm_backend());
+        GemmGroup grp(GEMM_BACKEND_FFMA);   // the update always runs the FFMA tiles: fp32 FMA accuracy (the stand-alone tcgen05 tiles keep one accumulator)
         for (int k = 0; k < 2; ++k) {
             const int l = L[k] - 1 - k_top;
             if (l < 0) continue;

@@ -81,9 +81,11 @@ class UpdateEngine:
         self.mb_cursor = torch.zeros(1, dtype=torch.int32, device=dev)
         ws_bytes = load().ppoaf_update_workspace_bytes(C.byref(cfg), self.batch_size)
         self.workspace = torch.zeros(ws_bytes + 256, dtype=torch.uint8, device=dev)
-        # The whole-epoch persistent kernel (csrc/fused_step.cu) is the default step engine wherever it applies
-        # (PPOAF_STEP=chain selects the launch-chain path: one CUDA graph of 8 launches per minibatch)
-        self.fused = (os.environ.get("PPOAF_STEP", "fused") != "chain" and self.peer is None and cfg.world_size == 1
+        # PPOAF_STEP=fused selects the whole-epoch persistent kernel (csrc/fused_step.cu: tcgen05 3xTF32 tiles with A in
+        # TMEM, grid barriers instead of launch boundaries).  It is parity-green but measured slower than the launch chain
+        # at reference minibatch sizes, so the chain (one CUDA graph of 8 launches per minibatch) stays
+        # the default.
+        self.fused = (os.environ.get("PPOAF_STEP", "chain") == "fused" and self.peer is None and cfg.world_size == 1
                       and bool(load().ppoaf_ppo_fused_supported(C.byref(cfg))))
         self.fused_workspace = None
         if self.fused:

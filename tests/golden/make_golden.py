@@ -380,10 +380,96 @@ def gen_rollout_actions():
         print(name, {k: out[k].shape for k in out if k.startswith("s0/")})
 
 
+def gen_baseline_shapes():
+    """Full updates at the network / minibatch shapes of BASELINE.json's configs, through the
+    unmodified reference: C1 CartPole (baselines/gymnasium/cart_pole.py:30-65), C3 LunarLanderContinuous
+    (baselines/gymnasium/lunar_lander_continuous.py:33-68), C4 Humanoid (baselines/gymnasium/humanoid.py:46-76, both
+    nets 256-wide as in the bench) and C5 MPE simple_spread MAPPO (baselines/pettingzoo/mpe_simple_spread.py:29-104).
+    The synthetic observations are NOT stored (they are regenerated from `in_make_rollout_json` by make_rollout, which is
+    deterministic); what the reference's networks produced on them (values, actions, log-probs) is stored.  Parameters
+    are stored after the LAST epoch only, the status scalars and drawn indices for every epoch."""
+    import json
+    cases = {
+        "shape_c1": dict(ro=dict(seed=51, T=256, E=1, obs_dim=4, n_discrete=2, max_ts_per_ep=32, p_term=0.03, p_trunc=0.0,
+                                 obs_scale=False),
+                         net=dict(act="leaky_relu", actor_hidden=128, critic_hidden=128), pol=dict(lr=2e-3), B=256, epochs=10),
+        "shape_c3": dict(ro=dict(seed=53, T=32, E=64, obs_dim=8, act_dim=2, max_ts_per_ep=32, p_term=0.01, p_trunc=0.01,
+                                 obs_scale=False),
+                         net=dict(act="leaky_relu", actor_hidden=64, critic_hidden=256), pol=dict(lr=3e-4), B=512, epochs=2),
+        "shape_c4": dict(ro=dict(seed=54, T=16, E=64, obs_dim=376, act_dim=17, max_ts_per_ep=16, p_term=0.01, p_trunc=0.01,
+                                 obs_scale=False),
+                         net=dict(act="tanh", actor_hidden=256, critic_hidden=256, dist_range=0.4), pol=dict(lr=1e-4),
+                         B=512, epochs=2),
+        "shape_c5": dict(ro=dict(seed=55, T=32, E=8, agents=("a0", "a1", "a2"), obs_dim=18, critic_obs_dim=54, n_discrete=5,
+                                 max_ts_per_ep=64, p_term=0.01, p_trunc=0.01, obs_scale=False, shared_critic_obs=True),
+                         net=dict(act="leaky_relu", actor_hidden=128, critic_hidden=256), pol=dict(lr=3e-4), B=128, epochs=2),
+    }
+    for name, c in cases.items():
+        ro = make_rollout(**c["ro"])
+        torch.manual_seed(1000 + c["ro"]["seed"])
+        pol = build_policy(ro, **c["net"], **c["pol"])
+        fill_policy_outputs(pol, ro, seed=2000 + c["ro"]["seed"])
+        seg = run_reference_rollout(pol, ro)
+        pid = "pol"
+        ppo = object.__new__(PPO)
+        ppo.policies = {pid: pol}
+        ppo.normalize_values = True
+        ppo.normalize_adv = True
+        ppo.value_normalizers = {pid: RunningStatNormalizer(pid + "-value_normalizer", torch.device("cpu"))}
+        ppo.status_dict = {pid: {}, "global status": {"iteration": 0, "timesteps": 0}}
+        ppo.user_huber_loss = pol.use_huber_loss
+        out = {}
+        for prefix, net in (("init/actor", pol.actor), ("init/critic", pol.critic)):
+            for k, v in net.state_dict().items():
+                out[f"{prefix}/param/{k}"] = v.detach().numpy().copy()
+        rec = _RecordingDataset(pol.dataset)
+        loader = DataLoader(rec, batch_size=c["B"], shuffle=True)
+        perm_seed = 3000 + c["ro"]["seed"]
+        torch.manual_seed(perm_seed)
+        pol.train()
+        for ep in range(c["epochs"]):
+            rec.drawn = []
+            ppo._ppo_batch_train(loader, pid)
+            out[f"ep{ep}/batch_idxs"] = np.array(rec.drawn, dtype=np.int64)
+            sd = ppo.status_dict[pid]
+            out[f"ep{ep}/status"] = np.array([sd["actor loss"], sd["critic loss"], sd["kl avg"],
+                                              sd["weighted entropy"]], dtype=np.float64)
+            rs = ppo.value_normalizers[pid].running_stats
+            out[f"ep{ep}/vn"] = np.array([float(rs.mean), float(rs.variance), float(rs.count)])
+        last = c["epochs"] - 1
+        for prefix, net in ((f"ep{last}/actor", pol.actor), (f"ep{last}/critic", pol.critic)):
+            for k, v in net.state_dict().items():
+                out[f"{prefix}/param/{k}"] = v.detach().numpy().copy()
+        out[f"ep{last}/dataset_values"] = pol.dataset.values.numpy().copy()
+        hp = dict(B=c["B"], epochs=c["epochs"], perm_seed=perm_seed, lr=pol.lr(),
+                  entropy_weight=pol.entropy_weight(), surr_clip=pol.surr_clip,
+                  vf_clip=np.nan if pol.vf_clip is None else pol.vf_clip,
+                  gradient_clip=np.nan if pol.gradient_clip is None else pol.gradient_clip,
+                  kl_loss_weight=pol.kl_loss_weight, use_huber_loss=bool(pol.use_huber_loss),
+                  normalize_adv=True, normalize_values=True,
+                  activation=np.array(c["net"]["act"]), gamma=pol.gamma, lambd=pol.lambd,
+                  dist_range=c["net"].get("dist_range", 1.0),
+                  actor_hidden=c["net"]["actor_hidden"], critic_hidden=c["net"]["critic_hidden"], depth=3)
+        ins = rollout_inputs(ro)
+        for k in list(ins):                                   # regenerated from the seed at test time
+            if k.split("/")[0] in ("in_obs", "in_next_obs", "in_critic_obs", "in_rewards"):
+                del ins[k]
+        ro_kw = dict(c["ro"])
+        if "agents" in ro_kw:
+            ro_kw["agents"] = list(ro_kw["agents"])
+        ins["in_make_rollout_json"] = np.array(json.dumps(ro_kw))
+        np.savez_compressed(os.path.join(HERE, name + ".npz"), **ins,
+                            ds_advantages=seg["advantages"], ds_rewards_to_go=seg["rewards_to_go"], ds_ep_lens=seg["ep_lens"],
+                            **out, **{"hp_" + k: v for k, v in hp.items()})
+        print(name, "N =", len(seg["advantages"]), {k: out[k] for k in out if k.endswith("status")})
+
+
 if __name__ == "__main__":
     import sys
     if len(sys.argv) > 1 and sys.argv[1] == "actions":       # only the rollout-action fixtures (added later)
         gen_rollout_actions()
+    elif len(sys.argv) > 1 and sys.argv[1] == "shapes":      # only the BASELINE-shape update fixtures (added in round 2)
+        gen_baseline_shapes()
     elif len(sys.argv) > 1 and sys.argv[1] == "edges":       # only the edge-shape segment fixtures (added later)
         gen_segments(only=("seg_len1", "seg_open", "seg_max1"))
     else:
@@ -391,3 +477,4 @@ if __name__ == "__main__":
         gen_stats()
         gen_updates()
         gen_rollout_actions()
+        gen_baseline_shapes()

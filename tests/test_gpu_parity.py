@@ -20,16 +20,26 @@ SEG_CASES = ["seg_single", "seg_multi", "seg_bsclip", "seg_nogae", "seg_dynclip"
              "seg_len1", "seg_open", "seg_max1"]          # edge shapes: all length-1, never-ending, cut at every step
 
 
-@pytest.fixture(params=["fused", "ffma", "tcgen05"])
+@pytest.fixture(params=["ffma", "fused"])
 def gemm_backend(request, monkeypatch):
-    """Run a test on every engine of the minibatch step: the persistent whole-epoch kernel (tcgen05 3xTF32 tiles, the
-    default) and the launch-chain path with FFMA tiles or tcgen05 tiles."""
+    """Run a test on both engines of the minibatch step: the launch chain with FFMA tiles (default) and the persistent
+    whole-epoch kernel (PPOAF_STEP=fused: tcgen05 3xTF32 tiles, A operand in TMEM, split accumulators)."""
     from ppo_and_friends_b200 import ops
     if request.param == "fused":
         monkeypatch.setenv("PPOAF_STEP", "fused")
         yield request.param
         return
     monkeypatch.setenv("PPOAF_STEP", "chain")
+    ops.set_gemm_backend(request.param)
+    yield request.param
+    ops.set_gemm_backend("ffma")
+
+
+@pytest.fixture(params=["ffma", "tcgen05"])
+def fwd_backend(request):
+    """Forward-only GEMM launches (ppoaf_mlp_forward): FFMA tiles, or the stand-alone tcgen05 tiles of umma.cuh (single
+    accumulator: fine for a forward pass, not used by the update)."""
+    from ppo_and_friends_b200 import ops
     ops.set_gemm_backend(request.param)
     yield request.param
     ops.set_gemm_backend("ffma")
@@ -231,7 +241,7 @@ def test_normalize_clip_vs_oracle(n, dim):
                                            ([4, 128, 128, 128, 2], "leaky_relu", 3), ([5, 3], "tanh", 9),
                                            # reduction longer than one staged round (K > 512): gathered and plain layers
                                            ([700, 600, 3], "tanh", 70), ([1030, 40], "relu", 33)])
-def test_mlp_forward_vs_torch_fp32(dims, act, rows, gemm_backend):
+def test_mlp_forward_vs_torch_fp32(dims, act, rows, fwd_backend):
     from oracle.update import ACTIVATIONS
     from ppo_and_friends_b200 import _lib, ops
     torch.manual_seed(sum(dims))
@@ -360,6 +370,40 @@ def test_update_matches_reference(name, use_graphs, monkeypatch, gemm_backend):
             rs = state.value_normalizers["pol"].running_stats
             np.testing.assert_allclose([float(rs.mean), float(rs.variance), rs.count], g[f"ep{ep}/vn"], rtol=1e-5)
         np.testing.assert_allclose(ds.values.cpu().numpy(), g[f"ep{ep}/dataset_values"], rtol=1e-4, atol=1e-5)
+
+
+SHAPE_CASES = ["shape_c1", "shape_c3", "shape_c4", "shape_c5"]      # BASELINE.json config shapes
+
+
+@pytest.mark.parametrize("name", SHAPE_CASES)
+def test_update_matches_reference_at_baseline_shapes(name, gemm_backend):
+    """Full updates at the BASELINE network / minibatch shapes (C1 CartPole 4-128^3-2 B=256 x 10 epochs; C3
+    LunarLanderContinuous 8-64^3-2 / 8-256^3-1 B=512; C4 Humanoid 376-256^3-17 B=512; C5 MPE MAPPO 18-128^3-5 / 54-256^3-1,
+    3 agents, B=128) against goldens recorded from the UNMODIFIED reference: drawn indices bit-exact, status scalars of
+    every epoch and the parameters after the last epoch within 1e-4."""
+    from ppo_and_friends_b200.ppo import PPOUpdateState, _Loader, ppo_batch_train
+    g = load_golden(name)
+    ro, pol = policy_from_update_golden(g)
+    ds = run_device_rollout(pol, ro)
+    assert np.array_equal(ds.ep_lens, g["ds_ep_lens"])
+    np.testing.assert_allclose(ds.advantages.cpu().numpy(), g["ds_advantages"], rtol=1e-5, atol=1e-5)
+    n_ep = int(g["hp_epochs"])
+    state = PPOUpdateState({"pol": pol}, batch_size=int(g["hp_B"]), epochs_per_iter=n_ep)
+    torch.manual_seed(int(g["hp_perm_seed"]))
+    loader = _Loader(ds, int(g["hp_B"]))
+    for ep in range(n_ep):
+        ppo_batch_train(state, loader, "pol")
+        assert np.array_equal(pol._engine._perm_dev.cpu().numpy(), g[f"ep{ep}/batch_idxs"])
+        sd = state.status_dict["pol"]
+        got = np.array([sd["actor loss"], sd["critic loss"], sd["kl avg"], sd["weighted entropy"]])
+        assert rel_err(got, g[f"ep{ep}/status"], 1e-3) < 1e-4, (ep, got, g[f"ep{ep}/status"])
+        rs = state.value_normalizers["pol"].running_stats
+        np.testing.assert_allclose([float(rs.mean), float(rs.variance), rs.count], g[f"ep{ep}/vn"], rtol=1e-5)
+    for net, obj in (("actor", pol.actor), ("critic", pol.critic)):
+        for k, v in obj.state_dict().items():
+            np.testing.assert_allclose(v.cpu().numpy(), g[f"ep{n_ep - 1}/{net}/param/{k}"], rtol=1e-4, atol=1e-6,
+                                       err_msg=f"{net}/{k}")
+    np.testing.assert_allclose(ds.values.cpu().numpy(), g[f"ep{n_ep - 1}/dataset_values"], rtol=1e-4, atol=1e-5)
 
 
 def test_update_vs_oracle_humanoid_shape(gemm_backend):
