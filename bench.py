@@ -14,10 +14,12 @@ One STEP = one pass of the hot path over one synthetic rollout shard per rank:
 `value` = env-steps/s with the rollout ring already resident in HBM; `e2e` = the same pass started
 from the pinned HOST ring (bulk H2D of the ring + segment table inside the timed region, D2H of the
 epoch statistics).  The GAE + normalisation microbench (BASELINE configs[1]: 2^22 timesteps, obs 376)
-runs on rank 0 in the same invocation and feeds `microbench` and `roofline` (HBM-bound kernels);
-`roofline_update` describes the update step itself (latency-bound at reference minibatch sizes).
-The CPU baseline is the oracle port (oracle/: numpy + torch-CPU restatement of the reference) timed
-on this box's host cores on a bounded sample; `--impl reference` prints that arm on its own.
+runs on rank 0 in the same invocation and feeds `microbench` (with its own HBM roofline); `roofline` describes the
+dominant kernel of the timed region, the grouped GEMM launches of the minibatch step.
+The CPU baseline is the UNMODIFIED reference (oracle/_ref: a git-ignored copy made by oracle/build_ref.py in the
+build container, which travels to the GPU box like the built .so) timed on this box's host cores on a bounded
+sample; the oracle port (oracle/) is reported beside it.  `--impl reference` prints the reference arm on its own,
+with --gpus N ranks over gloo.
 """
 import argparse
 import json
@@ -162,6 +164,7 @@ class HotPath:
         self.state = PPOUpdateState({"pol": pol}, batch_size=w["B"], epochs_per_iter=w["epochs"])
         self.n = ro.T * ro.E * len(ro.agents)
         self.n_mb = (self.n + w["B"] - 1) // w["B"]
+        self.h2d_events = []
 
     def step(self, from_host=False):
         from ppo_and_friends_b200.ppo import train_policies
@@ -169,7 +172,11 @@ class HotPath:
         if from_host:                                     # e2e: the pinned host ring crosses PCIe inside the timed region
             ring = pol._ring
             used = int(ring.steps.max())
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
             ring.dev[:used].copy_(ring.host[:used], non_blocking=True)
+            e1.record()
+            self.h2d_events.append((e0, e1))
         pol.initialize_dataset()
         pol.dataset.ring = pol._ring
         pol.dataset._seg = self.seg
@@ -207,6 +214,46 @@ def flops_per_sample_visit(w):
     a = pmm([w["Do"]] + [w["actor_hidden"]] * 3 + [pred])
     c = pmm([w["Dc"]] + [w["critic_hidden"]] * 3 + [1])
     return 6 * (a + c)
+
+
+def measure_fp32_peak(n=4096, iters=5):
+    """cuBLAS SGEMM with TF32 off: the fp32 FMA throughput this GPU sustains (the pipe the update's GEMM tiles run on)."""
+    prev = torch.backends.cuda.matmul.allow_tf32
+    torch.backends.cuda.matmul.allow_tf32 = False
+    try:
+        a = torch.randn(n, n, device="cuda"); b = torch.randn(n, n, device="cuda")
+        torch.matmul(a, b); torch.cuda.synchronize()
+        best = 1e9
+        for _ in range(iters):
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record(); torch.matmul(a, b); e1.record(); torch.cuda.synchronize()
+            best = min(best, e0.elapsed_time(e1))
+        return 2.0 * n ** 3 / (best * 1e-3) / 1e12
+    finally:
+        torch.backends.cuda.matmul.allow_tf32 = prev
+
+
+def kernel_shares(hp):
+    """Device time per kernel name over one hot-path step (untimed, after the measurement), from CUPTI activity records."""
+    try:
+        from torch.profiler import ProfilerActivity, profile
+        hp.step(False); torch.cuda.synchronize()
+        with profile(activities=[ProfilerActivity.CUDA]) as prof:
+            hp.step(False)
+            torch.cuda.synchronize()
+        kernels, total = {}, 0.0
+        for e in prof.key_averages():
+            us = float(getattr(e, "device_time_total", 0.0) or getattr(e, "cuda_time_total", 0.0))
+            if us <= 0 or "memcpy" in e.key.lower() or "memset" in e.key.lower():
+                continue
+            kernels[e.key[:96]] = {"us": us, "count": int(e.count)}
+            total += us
+        if not kernels:
+            return None
+        top = dict(sorted(kernels.items(), key=lambda kv: -kv[1]["us"])[:8])
+        return {"total_us": total, "kernels": top}
+    except Exception:
+        return None
 
 
 def time_steps(fn, steps, warmup, flush):
@@ -380,23 +427,47 @@ def workload_label(w):
             f"B={w['B']}, epochs={w['epochs']}, KL early stop off)")
 
 
+def reference_available():
+    sys.path.insert(0, os.path.join(ROOT, "tests", "golden"))
+    try:
+        import ref_harness
+        return ref_harness.available()
+    except Exception:
+        return False
+
+
 def run_reference_arm(args, w):
+    """`--impl reference`: the UNMODIFIED reference (oracle/_ref) on the host cores, args.gpus ranks over gloo (one process
+    per rank, spawned here by rank 0), on our arm's workload.  Falls back to the oracle port only when the reference copy is
+    missing."""
     rank, world, _ = dist_env()
     if rank != 0:
         return
-    for _ in range(args.warmup):
-        cpu_reference_sample(w, sample_minibatches=2)
-    vals, secs = [], 0.0
-    for _ in range(args.steps):
-        res, t = cpu_reference_sample(w, sample_minibatches=64)
-        vals.append(res["value"]); secs += t
-    v = float(np.mean(vals))
-    res["value"] = v
+    R = max(int(args.gpus), 1)
+    if reference_available():
+        from oracle import ref_bench
+        steps = max(1, min(args.steps, 5))                      # bounded: a CPU step takes seconds (tens of seconds at R = 8)
+        wu = 1 if args.warmup > 0 else 0
+        res = ref_bench.run(w, n_ranks=R, steps=steps, warmup=wu, epochs_timed=1)
+        v, secs = res["value"], res["per_step_s"]
+        note = ("unmodified reference on the host cores: value = ranks x shard env-steps / slowest rank's step time; "
+                f"{steps} timed step(s) after {wu} warm-up step(s)")
+    else:
+        steps = args.steps
+        for _ in range(args.warmup):
+            cpu_reference_sample(w, sample_minibatches=2)
+        vals, tot = [], 0.0
+        for _ in range(steps):
+            res, t = cpu_reference_sample(w, sample_minibatches=64)
+            vals.append(res["value"]); tot += t
+        v = float(np.mean(vals)) * R
+        res["value"] = v
+        secs = tot / steps
+        note = "oracle port (the reference copy oracle/_ref is missing); single-rank figure scaled by the rank count"
     line = {"impl": "reference", "metric": "ppo_update_env_steps_per_s", "value": v, "unit": "env-steps/s",
-            "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * secs / args.steps,
+            "n_gpus": args.gpus, "steps": steps, "warmup": args.warmup, "ms_per_step": 1e3 * secs,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": workload_label(w), "note": "oracle port of the reference CPU path on the host cores; "
-                       "value extrapolated from a bounded sample per step (see cpu_baseline.sample)"},
+            "config": {"workload": workload_label(w), "note": note},
             "cpu_baseline": res, "e2e": {"value": v, "unit": "env-steps/s", "h2d_bytes_per_step": 0,
                                          "d2h_bytes_per_step": 0}, "gpu_launches": 0}
     print(json.dumps(line))
@@ -434,7 +505,8 @@ def main():
     sampler.start()
     ms = time_steps(lambda: hp.step(False), args.steps, args.warmup, flush)
     clocks = sampler.stop()
-    ms_e2e = time_steps(lambda: hp.step(True), args.steps, 1, flush)
+    ms_e2e = time_steps(lambda: hp.step(True), args.steps, args.warmup, flush)
+    h2d_ms = float(np.mean([a.elapsed_time(b) for a, b in hp.h2d_events[-args.steps:]]))   # the ring copy alone, per step
 
     env_steps = w["ts"] * w["E"] * world                    # multi-agent: env steps exclude the xA factor
     value = env_steps * args.steps / (ms / 1e3)
@@ -453,16 +525,37 @@ def main():
                                                           f"{ring_mb:.0f} MB", "peaks": pk["source"]},
             "clocks": clocks,
             "e2e": {"value": e2e, "unit": "env-steps/s", "h2d_bytes_per_step": hp.h2d_bytes(),
-                    "d2h_bytes_per_step": hp.d2h_bytes(), "ms_per_step": ms_e2e / args.steps},
+                    "d2h_bytes_per_step": hp.d2h_bytes(), "ms_per_step": ms_e2e / args.steps, "h2d_ms": h2d_ms,
+                    "h2d_gbs": hp.h2d_bytes() / h2d_ms / 1e6,
+                    "note": "same pass started from the pinned host ring; h2d_ms = CUDA-event time of the ring copy alone"},
             "gpu_launches": hp.launches_per_step() * args.steps,
-            "roofline_update": {"bound": "latency", "achieved": upd_tflops, "peak": pk["bf16_tflops_sustained"],
-                                "unit": "TFLOP/s", "frac": upd_tflops / pk["bf16_tflops_sustained"], "traffic": None,
-                                "note": f"{flops_step / 1e9:.2f} GFLOP per minibatch step (6*P_mm*B) over the measured "
-                                        f"{us_per_mb:.1f} us step: serial-latency bound at B={w['B']}, not a dense "
-                                        "tensor-core contraction (SURVEY.md §8d)"}}
+            }
+    # live per-kernel device time of one extra (untimed) step: kernels replayed from CUDA graphs have no event of their own,
+    # so their durations come from CUPTI activity records (torch.profiler); fallback: the share of the committed launch list
+    shares = kernel_shares(hp) if rank == 0 else None
+    gk = None
+    if shares:
+        gk = next((v for k, v in shares["kernels"].items() if "grouped_gemm_kernel" in k), None)
+    gemm_share = (gk["us"] / shares["total_us"]) if gk else 0.80
+    fp32 = measure_fp32_peak() if rank == 0 else None
+    line["roofline"] = {
+        "bound": "tensor", "kernel": "grouped_gemm_kernel (6 of the 8 launches of a minibatch step)",
+        "achieved": upd_tflops / gemm_share, "peak": pk["bf16_tflops_sustained"], "unit": "TFLOP/s",
+        "frac": upd_tflops / gemm_share / pk["bf16_tflops_sustained"], "traffic": None,
+        "algorithmic_flops_per_step": flops_step, "step_us": us_per_mb, "whole_step_tflops": upd_tflops,
+        "fp32_peak_tflops_measured": fp32, "frac_of_fp32_peak": (upd_tflops / gemm_share / fp32) if fp32 else None,
+        "kernel_share_of_step": gemm_share, "kernel_avg_launch_us": (gk["us"] / gk["count"]) if gk else None,
+        "kernel_launches_per_step": (gk["count"]) if gk else None,
+        "share_source": "CUPTI activity records of one extra untimed step (torch.profiler)" if gk else "profiles/r01_launches_c4_summary.txt",
+        "step_kernels": shares["kernels"] if shares else None,
+        "note": f"dominant kernel of the timed region: {flops_step / 1e9:.2f} GFLOP per minibatch step (6*P_mm*B, SURVEY.md §8d) over "
+                f"{gemm_share:.2f} x the CUDA-event step time of {us_per_mb:.1f} us (the kernel's share comes from the committed "
+                "launch list; it runs inside a CUDA graph, so it has no event of its own).  The kernel is fp32 FFMA: the tensor peak "
+                f"({pk['source']} bf16 sustained) is the contract's denominator, fp32_peak_tflops_measured (cuBLAS SGEMM 4096^3, TF32 "
+                "off, measured in this run) the pipe it actually uses.  At B=512 the step is a chain of 8 dependent launches of "
+                "~40-270 MFLOP each: latency-bound, see DESIGN.md §3.3-3.4"}
     if rank == 0 and world == 1 and not args.no_microbench:
         mb = microbench_c2(pk)
-        line["microbench"] = mb
         dom = max(mb["pieces"].items(), key=lambda kv: kv[1]["ms"])
         traffic = None
         tpath = os.path.join(ROOT, "profiles", "r01_c2_traffic.json")      # dram bytes per launch from the ncu --set full capture
@@ -470,14 +563,19 @@ def main():
             k = json.load(open(tpath))["kernels"].get(dom[0])
             if k:
                 traffic = k["dram_bytes_read"] + k["dram_bytes_write"]
-        line["roofline"] = {"bound": "hbm", "achieved": dom[1]["gbs"], "peak": pk["hbm_gbs"], "unit": "GB/s",
-                            "frac": dom[1]["gbs"] / pk["hbm_gbs"], "traffic": traffic, "algorithmic_bytes": dom[1]["bytes"],
-                            "kernel": dom[0],
-                            "note": f"dominant HBM kernel of the GAE+normalisation microbench; peak = {pk['source']} copy bandwidth"}
-    else:
-        line["roofline"] = line["roofline_update"]
+        mb["roofline"] = {"bound": "hbm", "achieved": dom[1]["gbs"], "peak": pk["hbm_gbs"], "unit": "GB/s",
+                          "frac": dom[1]["gbs"] / pk["hbm_gbs"], "traffic": traffic, "algorithmic_bytes": dom[1]["bytes"],
+                          "kernel": dom[0],
+                          "note": f"dominant HBM kernel of the GAE+normalisation microbench; peak = {pk['source']} copy bandwidth"}
+        line["microbench"] = mb
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
-        line["cpu_baseline"], _ = cpu_reference_sample(w, sample_minibatches=256)
+        port, _ = cpu_reference_sample(w, sample_minibatches=64)
+        if reference_available():
+            from oracle import ref_bench
+            line["cpu_baseline"] = ref_bench.run(w, n_ranks=1, steps=1, warmup=0, epochs_timed=1)
+            line["cpu_baseline_port"] = port
+        else:
+            line["cpu_baseline"] = port
     if rank == 0:
         print(json.dumps(line))
     if world > 1:

@@ -8,7 +8,7 @@ namespace ppoaf {
 enum { GEMM_BACKEND_FFMA = 0, GEMM_BACKEND_TCGEN05 = 1 };
 int gemm_backend();             // PPOAF_GEMM=ffma|tcgen05 (default tcgen05: 3xTF32 tensor-core tiles)
 struct GroupedGemmArgs;
-constexpr int kMaxGroupHost = 16;   // problems one grouped launch carries (== kMaxGroup of mlp.cuh)
+constexpr int kMaxGroupHost = 6;    // problems one grouped launch carries (== kMaxGroup of mlp.cuh)
 struct GemmGroup {
     GroupedGemmArgs* args;      // owned
     int n_tiles;

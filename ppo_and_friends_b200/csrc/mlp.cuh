@@ -47,7 +47,7 @@ __device__ __forceinline__ float act_bwd_from_out(float y, int act) {
 }
 
 enum { EPI_FWD = 0, EPI_BWD_X = 1, EPI_BWD_W = 2 };
-constexpr int kMaxGroup = 16;
+constexpr int kMaxGroup = 6;
 
 struct GemmProblem {
     const float* A; const float* B; float* C;

@@ -17,13 +17,18 @@
 // peer has passed barrier 1 of the step in between — no second cross-GPU barrier is needed.
 // A spin that exceeds ~2 s sets an error flag and returns instead of hanging the GPU.
 #include "internal.h"
+#include <stdlib.h>
 
 namespace ppoaf {
 
 constexpr int kPeerThreads = 1024;
 constexpr int kPeerMaxRanks = 8;
 constexpr int kPeerMaxVec = 2;            // float4 slots per thread held in registers (1 for a 460 K-parameter policy)
-constexpr long long kSpinLimit = 4000000000LL;   // ~2 s of SM clock
+// Spin budget of the cross-GPU barriers in SM clocks (PPOAF_PEER_TIMEOUT_S, default 30 s at ~2 GHz).  The host enqueues a
+// stream-level collective before the first exchange of every epoch (ppo.py), so the ranks enter the epoch together; the
+// budget only has to cover the skew that builds up inside one epoch.
+__device__ long long g_spin_limit = 60000000000LL;
+#define kSpinLimit g_spin_limit
 
 #ifdef PPOAF_PEER_TIMING
 __device__ long long g_peer_stamps[16];
@@ -31,6 +36,18 @@ __device__ long long g_peer_stamps[16];
 #else
 #define PEER_STAMP(k) do {} while (0)
 #endif
+
+static void configure_spin_limit() {
+    static bool done = false;
+    if (done) return;
+    done = true;
+    const char* e = getenv("PPOAF_PEER_TIMEOUT_S");
+    if (!e) return;
+    const double sec = atof(e);
+    if (sec <= 0.0) return;
+    const long long clk = (long long)(sec * 2.0e9);
+    cudaMemcpyToSymbol(g_spin_limit, &clk, sizeof(clk));
+}
 
 struct PeerArgs {
     const float* peer_grads[kPeerMaxRanks];   // the slot holding rank r's gradients for THIS parity (index = rank)
@@ -471,6 +488,7 @@ using namespace ppoaf;
 
 // ---- peer-memory plumbing (cudaMalloc + CUDA IPC; the handles travel through torch.distributed) ----------
 extern "C" int ppoaf_peer_alloc(size_t bytes, void** out) {
+    configure_spin_limit();            // set-up call: never inside a stream capture
     PPOAF_CHECK_ARG(out != nullptr && bytes > 0, "ppoaf_peer_alloc: bad arguments");
     cudaError_t e = cudaMalloc(out, bytes);
     PPOAF_CHECK_ARG(e == cudaSuccess, "ppoaf_peer_alloc: cudaMalloc failed: %s", cudaGetErrorString(e));
@@ -548,7 +566,7 @@ extern "C" int ppoaf_debug_peer_stamps(long long* out_host) {
 #endif
 
 // ---- NVLS variant ------------------------------------------------------------------------------------------------
-extern "C" size_t ppoaf_nvls_ctrl_bytes(void) {
+extern "C" size_t ppoaf_nvls_ctrl_bytes(void) { configure_spin_limit();
     return size_t(sm_count()) * 2 * sizeof(double) + 2 * peer_arrive_bytes() + 256;
 }
 extern "C" size_t ppoaf_nvls_flag_block_bytes(void) { return 256; }

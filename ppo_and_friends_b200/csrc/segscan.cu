@@ -312,6 +312,7 @@ extern "C" int ppoaf_build_flat_map(const int32_t* seg_col, const int32_t* seg_t
                                     int32_t n_cols, int64_t n_flat, int32_t* src_row, uint8_t* seg_flag,
                                     void* stream) {
     PPOAF_CHECK_ARG(n_seg >= 0 && n_cols > 0 && n_flat >= 0, "ppoaf_build_flat_map: bad sizes");
+    PPOAF_CHECK_ARG(n_flat < (int64_t(1) << 31), "ppoaf_build_flat_map: ring rows are int32: n_flat must stay below 2^31");
     if (n_seg == 0) return 0;
     const int threads = 256;
     int64_t blocks = ceil_div64(int64_t(n_seg) * 32, threads);

@@ -92,6 +92,7 @@ class UpdateEngine:
             fbytes = load().ppoaf_ppo_fused_workspace_bytes(C.byref(cfg), self.batch_size)
             self.fused_workspace = torch.zeros(fbytes + 256, dtype=torch.uint8, device=dev)   # barrier words start at zero
         self.null_state = torch.tensor([0.0, 1.0, 1e-4], dtype=torch.float64, device=dev)
+        self._sync_word = torch.zeros(1, dtype=torch.float32, device=dev)
         self._graphs = {}
         self._spec_perm = None          # (n, rng state before, rng state after, permutation) drawn ahead of time
         self._graph_key = None
@@ -176,6 +177,15 @@ class UpdateEngine:
             self._graphs.clear()
         return n_mb
 
+    def _ptr_key(self, ds, grads):
+        """Every device address a captured step bakes in (a key over a subset lets a stale graph replay
+        against freed memory when the caching allocator moves only some of the dataset tensors)."""
+        nets = self.policy.nets
+        return tuple(t.data_ptr() for t in (
+            ds.observations, ds.critic_observations, ds.raw_actions, ds.advantages, ds.log_probs, ds.rewards_to_go,
+            ds.values, self._perm_dev, self._mb_adv_stats, self._mb_val_stats, grads, nets.flat_params, nets.adam_m,
+            nets.adam_v, nets.adam_step, self.hparams, self.epoch_stats, self.mb_cursor, self.workspace)) + (len(ds),)
+
     def _capture(self, fn):
         graph = torch.cuda.CUDAGraph()
         torch.cuda.synchronize(self.device)
@@ -188,8 +198,8 @@ class UpdateEngine:
         if self.peer is not None and rows > 1:
             self.step_parity ^= 1                      # the peer gradient buffers alternate every real step
             self.policy.nets.flat_grads = self.peer.grads[parity]
-        key = (rows, parity, ds.observations.data_ptr(), ds.critic_observations.data_ptr(), ds.values.data_ptr(),
-               ds.advantages.data_ptr())
+        grads = self.peer.grads[parity] if self.peer is not None else self.policy.nets.flat_grads
+        key = (rows, parity) + self._ptr_key(ds, grads)
         if not self.use_graphs or rows < 2:
             self._step_eager(self._bufs(ds, rows, parity), parity)
             return
@@ -215,8 +225,8 @@ class UpdateEngine:
         this removes the graph-launch gap between steps and lets the programmatic dependencies span step boundaries
         (the first forward GEMM of step k+1 sets up while the optimizer of step k drains)."""
         start = self.step_parity if self.peer is not None else 0
-        key = ("epoch", n_full, start, ds.observations.data_ptr(), ds.critic_observations.data_ptr(),
-               ds.values.data_ptr(), ds.advantages.data_ptr())
+        grads = self.peer.grads[start] if self.peer is not None else self.policy.nets.flat_grads
+        key = ("epoch", n_full, start) + self._ptr_key(ds, grads)
         g = self._graphs.get(key)
         if g is None:
             if len(self._graphs) > 16:
@@ -274,6 +284,10 @@ class UpdateEngine:
             state = self.value_normalizer.running_stats.state if self.value_normalizer is not None else self.null_state
             check(lib.ppoaf_value_stats_sequence(ptr(state), ptr(triples), triples.shape[0], n_mb, 1e-8,
                                                  ptr(self._mb_val_stats), stream_ptr()), "ppoaf_value_stats_sequence")
+        elif self.peer is not None:
+            # no collective precedes the first gradient exchange of this epoch: line the ranks up on the stream, so the
+            # spin budget of the in-kernel cross-GPU barrier only has to cover the skew inside one epoch
+            mpi_utils.allreduce_sum_(self._sync_word)
         self.epoch_stats.zero_()
         self.mb_cursor.zero_()
         n_full = n // self.batch_size
@@ -328,14 +342,15 @@ def ppo_batch_train(ppo, data_loader, policy_id):
         mpi_utils.abort("ERROR: evaluate value or action prediction contains nan values!")
     if st[ST["BAD_RATIO"]] > 0:
         mpi_utils.abort("ERROR: ratios are nan or inf!")
-    if eng.peer is not None and eng.peer.error_flag() != 0:
-        mpi_utils.abort("ERROR: a rank did not reach the gradient exchange (peer barrier timed out)")
-    sums = np.array([st[ST["COUNTER"]], st[ST["ENTROPY"]], st[ST["ACTOR_LOSS"]], st[ST["CRITIC_LOSS"]], st[ST["KL"]]])
+    peer_err = float(eng.peer.error_flag() != 0) if eng.peer is not None else 0.0
+    sums = np.array([st[ST["COUNTER"]], st[ST["ENTROPY"]], st[ST["ACTOR_LOSS"]], st[ST["CRITIC_LOSS"]], st[ST["KL"]], peer_err])
     if mpi_utils.get_num_procs() > 1:                                   # ppo.py:2471-2475, one packed all-reduce
         t = torch.as_tensor(sums).to(policy.device)
         mpi_utils.allreduce_sum_(t)
         sums = t.cpu().numpy()
-    counter, total_entropy, total_actor, total_critic, total_kl = sums
+    if sums[5] > 0:                       # the flag travels with the statistics, so EVERY rank aborts (comm.Abort semantics)
+        mpi_utils.abort("ERROR: a rank did not reach the gradient exchange (peer barrier timed out)")
+    counter, total_entropy, total_actor, total_critic, total_kl = sums[:5]
     w_entropy = total_entropy * policy.entropy_weight()
     sd = ppo.status_dict[policy_id]
     sd["weighted entropy"] = w_entropy / counter

@@ -70,6 +70,10 @@ class RolloutRing:
                 self.copy_stream.synchronize()
             host[:self.capacity].copy_(self.host)
             dev[:self.capacity].copy_(self.dev)
+        if self.copy_stream is not None:
+            # the zero-fill / carry-over above ran on the current stream; the per-step H2D copies run on copy_stream and
+            # must not be overtaken by them
+            self.copy_stream.wait_stream(torch.cuda.current_stream(self.device))
         self.host, self.dev, self.capacity = host, dev, capacity
         self.host_np = self.host.numpy()
 
@@ -147,6 +151,10 @@ class PPODataset(object):
 
     # -- A2: one closed segment ---------------------------------------------------------------------
     def add_segment(self, col, t0, length, terminal, ending_value, clipped_ending_reward, starting_ts, ending_ts):
+        if int(length) < 1:
+            # the reference never closes an empty episode (end_episodes runs after add_episode_info of the same step); an
+            # empty segment would shift the per-segment bootstrap values of every later segment in the scan
+            abort("ERROR: attempting to close an episode segment of length {}".format(length))
         s = self._seg
         s["col"].append(col); s["t0"].append(t0); s["length"].append(length); s["terminal"].append(bool(terminal))
         s["v_boot"].append(ending_value); s["r_boot"].append(clipped_ending_reward)

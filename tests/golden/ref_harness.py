@@ -15,7 +15,22 @@ import types
 
 import numpy as np
 
-REFERENCE_ROOT = os.environ.get("PPOAF_REFERENCE_ROOT", "/root/reference")
+_REPO = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+
+
+def _find_reference():
+    """/root/reference in the build container; on the GPU box the git-ignored copy made by oracle/build_ref.py."""
+    for cand in (os.environ.get("PPOAF_REFERENCE_ROOT"), "/root/reference", os.path.join(_REPO, "oracle", "_ref", "ppo_and_friends")):
+        if cand and os.path.isdir(cand) and os.path.exists(os.path.join(cand, "ppo.py")):
+            return cand
+    return os.environ.get("PPOAF_REFERENCE_ROOT", "/root/reference")
+
+
+REFERENCE_ROOT = _find_reference()
+
+
+def available():
+    return os.path.isdir(REFERENCE_ROOT) and os.path.exists(os.path.join(REFERENCE_ROOT, "ppo.py"))
 
 
 def _install_mpi_stub():
@@ -23,29 +38,69 @@ def _install_mpi_stub():
     MPI = types.ModuleType("mpi4py.MPI")
 
     class _Comm:
+        """COMM_WORLD stand-in.  Single process: identity.  When torch.distributed is initialised (gloo, the R-rank CPU
+        arm of bench.py) the calls the reference makes on this path (utils/mpi_utils.py:50-111, utils/stats.py:47-50,
+        ppo.py:2471-2475) are carried by the matching gloo collectives."""
+
+        @staticmethod
+        def _dist():
+            import torch.distributed as dist
+            return dist if dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1 else None
+
         def Get_rank(self):
-            return 0
+            d = self._dist()
+            return d.get_rank() if d else 0
 
         def Get_size(self):
-            return 1
+            d = self._dist()
+            return d.get_world_size() if d else 1
 
         def allreduce(self, x, op=None):
-            return x
+            d = self._dist()
+            if d is None:
+                return x
+            import torch
+            red = {"SUM": d.ReduceOp.SUM, "MAX": d.ReduceOp.MAX, "MIN": d.ReduceOp.MIN}[op or "SUM"]
+            if isinstance(x, np.ndarray):
+                t = torch.from_numpy(np.ascontiguousarray(x).copy())
+                d.all_reduce(t, op=red)
+                return t.numpy()
+            t = torch.tensor([x], dtype=torch.float64)
+            d.all_reduce(t, op=red)
+            return type(x)(t.item()) if isinstance(x, (int, float)) else t.item()
 
         def allgather(self, x):
-            return [x]
+            d = self._dist()
+            if d is None:
+                return [x]
+            out = [None] * d.get_world_size()
+            d.all_gather_object(out, x)
+            return out
 
         def Bcast(self, buf, root=0):
+            d = self._dist()
+            if d is None:
+                return None
+            import torch
+            t = torch.from_numpy(buf)
+            d.broadcast(t, src=root)
             return None
 
         def bcast(self, x, root=0):
-            return x
+            d = self._dist()
+            if d is None:
+                return x
+            box = [x]
+            d.broadcast_object_list(box, src=root)
+            return box[0]
 
         def barrier(self):
-            return None
+            d = self._dist()
+            if d is not None:
+                d.barrier()
 
         def Barrier(self):
-            return None
+            self.barrier()
 
         def Abort(self, code=1):
             raise RuntimeError("comm.Abort() called by the reference")
