@@ -79,6 +79,10 @@ class PPOPolicy:
                  **kw_args):
         if enable_icm:
             abort("ERROR: ICM is outside the B200 update path (SURVEY.md §2 row 11).")
+        if ac_network is not None and getattr(ac_network, "__name__", str(ac_network)) != "FeedForwardNetwork":
+            # the reference instantiates `ac_network` (policies/ppo_policy.py:390-446); only its FeedForwardNetwork
+            # (networks/ppo_networks/feed_forward.py) has a CUDA counterpart here, anything else must not be ignored
+            abort("ERROR: ac_network {} is outside the B200 update path (FeedForwardNetwork only).".format(ac_network))
         self.name = name
         self.action_space = action_space
         self.actor_obs_space = actor_observation_space
@@ -95,6 +99,10 @@ class PPOPolicy:
         self.gradient_clip, self.kl_loss_weight = gradient_clip, kl_loss_weight
         self.envs_per_proc = envs_per_proc
         self.agent_grouping = False
+        # read by PPO.__init__ (reference ppo.py:347-354); the base policy has no constraints (policies/ppo_policy.py:187-189)
+        self.have_step_constraints = False
+        self.have_reset_constraints = False
+        self.agent_shared_icm = False
         self.verbose = verbose
         self.use_huber_loss = use_huber_loss
         self.frozen = False
@@ -171,6 +179,31 @@ class PPOPolicy:
                       "actor_kw_args['distribution_min'/'distribution_max'].")
         broadcast_model_parameters(self.nets.flat_params)
         barrier()
+
+    def seed(self, seed):
+        """policies/ppo_policy.py:347-352 (called by PPO.__init__, ppo.py:595): seed the spaces (duck-typed)."""
+        for space in (self.action_space, self.actor_obs_space):
+            if hasattr(space, "seed"):
+                space.seed(seed)
+
+    def freeze(self):
+        """policies/ppo_policy.py:1322-1326 (ppo.py:661)."""
+        self.frozen = True
+
+    def unfreeze(self):
+        self.frozen = False
+
+    def apply_step_constraints(self, *args):
+        """policies/ppo_policy.py:1114-1135: the base policy constrains nothing."""
+        return args
+
+    def apply_reset_constraints(self, *args):
+        """policies/ppo_policy.py:1137-1150."""
+        return args
+
+    def shuffle_agent_ids(self):
+        """policies/ppo_policy.py:364-371 (only called for agent-grouping policies, ppo.py:1643-1644)."""
+        np.random.shuffle(self.agent_ids)
 
     @property
     def head(self):
@@ -318,6 +351,31 @@ class PPOPolicy:
         if discrete:
             lp_h = lp_h.unsqueeze(-1)
         return raw_h.numpy(), act_h.numpy(), lp_h
+
+    def get_inference_actions(self, obs, deterministic):
+        """
+        Environment actions only, for `ppoaf test` (reference policies/ppo_policy.py:796-888; ppo.py:972, 1023).
+        deterministic: tanh(mean) mapped to the action range (Gaussian, networks/distributions.py:596-631) or the arg-max
+        class (Categorical, :251-269); otherwise a sample drawn with the rollout protocol.
+        """
+        obs = np.asarray(obs) if not torch.is_tensor(obs) else obs
+        if len(obs.shape) < 2:
+            abort("ERROR: get_inference_actions expects a batch of observations but "
+                  "instead received shape {}.".format(tuple(obs.shape)))
+        if not deterministic:
+            return torch.as_tensor(self.get_rollout_actions(obs)[1])
+        t_obs = torch.as_tensor(obs, dtype=torch.float32).to(self.device).reshape(obs.shape[0], -1).contiguous()
+        discrete = self.action_dtype != "continuous"
+        action_pred = self.actor(t_obs, softmax_out=discrete)
+        if discrete:
+            return torch.argmax(action_pred, dim=-1).cpu()
+        n = t_obs.shape[0]
+        rescale = bool((self.dist_min != -1.0).any() or (self.dist_max != 1.0).any())
+        zeros = torch.zeros(n, self.action_dim, dtype=torch.float32, device=self.device)   # no noise: raw = mean
+        _, act, _ = ops.head_sample(self.head, action_pred, self.actor.state_dict()["distribution.log_std"], zeros,
+                                    self.min_std, self._dist_dev("min") if rescale else None,
+                                    self._dist_dev("max") if rescale else None, act_dim=self.action_dim)
+        return act.cpu()
 
     def _dist_dev(self, which):
         """The Gaussian head's output range as device tensors (built once)."""

@@ -108,7 +108,10 @@ class UpdateEngine:
         h[HP["GRAD_CLIP"]] = -1.0 if p.gradient_clip is None else float(p.gradient_clip)
         h[HP["KL_WEIGHT"]] = float(p.kl_loss_weight)
         h[HP["VF_CLIP"]] = -1.0 if p.vf_clip is None else float(p.vf_clip)
-        h[HP["BETA1"]], h[HP["BETA2"]], h[HP["ADAM_EPS"]] = 0.9, 0.999, 1e-5
+        # Adam's own hyper-parameters come from the optimizer view (reference: optim.Adam(..., eps=1e-5),
+        # policies/ppo_policy.py:341-345), so values restored by load_state_dict are honoured
+        g = p.actor_optim.param_groups[0]
+        h[HP["BETA1"]], h[HP["BETA2"]], h[HP["ADAM_EPS"]] = float(g["betas"][0]), float(g["betas"][1]), float(g["eps"])
         h[HP["INV_WORLD"]] = 1.0 / mpi_utils.get_num_procs()
         self.hparams.copy_(h, non_blocking=True)
 
