@@ -108,6 +108,18 @@ int ppoaf_normalize_clip(const float* x, int64_t n_rows, int32_t dim, const doub
 int ppoaf_denormalize(const float* x, int64_t n_rows, int32_t dim, const double* state, float eps,
                       float* y, void* stream);
 
+/* "Next" row 2: the reward normaliser's environment step, RewardNormalizer.step
+ * (environments/filter_wrappers.py:393-425) with its sequential-in-time semantics: running_reward[e] =
+ * running_reward[e] * gamma + rewards[e] for e = 0 .. E-1 IN ORDER, the whole partially updated vector entering the running
+ * statistics after every element.  ppoaf_reward_norm_triples writes the E batch triples (mean | M2 | n) of one step and
+ * zeroes running_reward where `dones`; the caller all-gathers them across ranks and integrates them with
+ * ppoaf_value_stats_sequence (n_mb = E), which pools the ranks per element exactly like the reference's allgather.
+ * ppoaf_reward_scale_clip: y = clip(r / sqrt(var + eps), lo, hi)  (:466-476, RewardClipper :700-719; lo >= hi: no clip). */
+int ppoaf_reward_norm_triples(const float* rewards, const uint8_t* dones, double* running_reward /* fp64 [E], in/out */,
+                              int32_t n_envs, double gamma, double* triples_out /* fp64 [E, 3] */, void* stream);
+int ppoaf_reward_scale_clip(const float* rewards, const double* state /* fp64 [3]: mean, var, count */, float eps,
+                            float lo, float hi, float* out, int32_t n, void* stream);
+
 /* ------------------------------------------------------------------------------------------
  * P1..P4  The minibatch update.
  * ---------------------------------------------------------------------------------------- */

@@ -73,6 +73,8 @@ _SIGNATURES = {
     "ppoaf_stats_merge": (C.c_int, [_P, _P, C.c_int32, C.c_int32, _P]),
     "ppoaf_normalize_clip": (C.c_int, [_P, C.c_int64, C.c_int32, _P, C.c_float, C.c_float, C.c_float, _P, _P]),
     "ppoaf_denormalize": (C.c_int, [_P, C.c_int64, C.c_int32, _P, C.c_float, _P, _P]),
+    "ppoaf_reward_norm_triples": (C.c_int, [_P, _P, _P, C.c_int32, C.c_double, _P, _P]),
+    "ppoaf_reward_scale_clip": (C.c_int, [_P, _P, C.c_float, C.c_float, C.c_float, _P, C.c_int32, _P]),
     "ppoaf_param_layout": (C.c_int64, [C.POINTER(MlpDesc), C.c_int32, C.POINTER(C.c_int64)]),
     "ppoaf_update_workspace_bytes": (C.c_size_t, [C.POINTER(UpdateCfg), C.c_int32]),
     "ppoaf_epoch_prepare": (C.c_int, [_P, _P, _P, C.c_int64, C.c_int32, _P, _P, _P]),

@@ -325,9 +325,66 @@ __global__ void value_stats_sequence_kernel(double* __restrict__ state, const do
     state[0] = mean; state[1] = var; state[2] = count;
 }
 
+// ---- reward normaliser, one environment step (reference environments/filter_wrappers.py:393-425) ----
+// The reference walks the E environments of a rank IN ORDER: running_reward[e] = running_reward[e] * gamma + r[e], and
+// after EVERY single-element change it feeds the WHOLE (partially updated) vector to RunningMeanStd.update — E statistic
+// updates per step.  The moments of a vector in which one element changed follow from the previous ones in O(1) (fp64),
+// so one thread produces the E batch triples (mean, M2, n = E) of a step; ppoaf_value_stats_sequence then pools them over
+// ranks and integrates them in (e, rank) order, exactly like the reference's allgather + concatenate inside the loop.
+__global__ void reward_norm_triples_kernel(const float* __restrict__ rewards, const uint8_t* __restrict__ dones,
+                                           double* __restrict__ running_reward, int E, double gamma,
+                                           double* __restrict__ triples) {
+    if (threadIdx.x != 0 || blockIdx.x != 0) return;
+    double mean = 0.0;
+    for (int e = 0; e < E; ++e) mean += running_reward[e];
+    mean /= double(E);
+    double m2 = 0.0;
+    for (int e = 0; e < E; ++e) { const double d = running_reward[e] - mean; m2 += d * d; }
+    for (int e = 0; e < E; ++e) {
+        const double old = running_reward[e];
+        const double nw = old * gamma + double(rewards[e]);
+        running_reward[e] = nw;
+        const double new_mean = mean + (nw - old) / double(E);
+        m2 += (nw - old) * ((nw - new_mean) + (old - mean));
+        if (m2 < 0.0) m2 = 0.0;
+        mean = new_mean;
+        triples[3 * e] = mean; triples[3 * e + 1] = m2; triples[3 * e + 2] = double(E);
+    }
+    for (int e = 0; e < E; ++e)
+        if (dones[e]) running_reward[e] = 0.0;               // filter_wrappers.py:420-425
+}
+
+// y = clip(r / sqrt(var + eps), lo, hi)  (filter_wrappers.py:466-476 followed by RewardClipper :700-719); lo >= hi: no clip
+__global__ void reward_scale_clip_kernel(const float* __restrict__ r, const double* __restrict__ state, float eps, float lo,
+                                         float hi, float* __restrict__ y, int n) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const double sd = sqrt(state[1] + double(eps));
+    float v = float(double(r[i]) / sd);
+    if (lo < hi) v = fminf(fmaxf(v, lo), hi);
+    y[i] = v;
+}
+
 }  // namespace ppoaf
 
 using namespace ppoaf;
+
+extern "C" int ppoaf_reward_norm_triples(const float* rewards, const uint8_t* dones, double* running_reward, int32_t n_envs,
+                                         double gamma, double* triples_out, void* stream) {
+    PPOAF_CHECK_ARG(n_envs > 0 && rewards && dones && running_reward && triples_out, "ppoaf_reward_norm_triples: bad arguments");
+    reward_norm_triples_kernel<<<1, 32, 0, (cudaStream_t)stream>>>(rewards, dones, running_reward, n_envs, gamma, triples_out);
+    PPOAF_CHECK_LAUNCH("ppoaf_reward_norm_triples");
+    return 0;
+}
+
+extern "C" int ppoaf_reward_scale_clip(const float* rewards, const double* state, float eps, float lo, float hi, float* out,
+                                       int32_t n, void* stream) {
+    PPOAF_CHECK_ARG(n >= 0, "ppoaf_reward_scale_clip: n < 0");
+    if (n == 0) return 0;
+    reward_scale_clip_kernel<<<(n + 127) / 128, 128, 0, (cudaStream_t)stream>>>(rewards, state, eps, lo, hi, out, n);
+    PPOAF_CHECK_LAUNCH("ppoaf_reward_scale_clip");
+    return 0;
+}
 
 extern "C" size_t ppoaf_moments_workspace_bytes(int64_t n_rows, int32_t dim) {
     if (n_rows <= 0 || dim <= 0) return 64;

@@ -464,10 +464,95 @@ def gen_baseline_shapes():
         print(name, "N =", len(seg["advantages"]), {k: out[k] for k in out if k.endswith("status")})
 
 
+class ReplayEnv:
+    """A vectorised multi-agent environment stand-in (the interface of the reference's VectorizedEnv as its filter
+    wrappers see it, environments/ppo_env_wrappers.py:24-147) that replays pre-generated raw step results."""
+
+    def __init__(self, data):
+        self.data = data
+        self.agent_ids = tuple(data["agents"])
+        self.observation_space = {a: sp.Box(-np.inf, np.inf, (data["obs_dim"],)) for a in self.agent_ids}
+        self.critic_observation_space = {a: sp.Box(-np.inf, np.inf, (data["critic_dim"],)) for a in self.agent_ids}
+        self.action_space = {a: sp.Discrete(2) for a in self.agent_ids}
+        self.null_actions = {a: 0 for a in self.agent_ids}
+        self.t = 0
+
+    def get_batch_size(self):
+        return self.data["E"]
+
+    def reset(self):
+        self.t = 0
+        return ({a: self.data[f"obs/{a}"][0].copy() for a in self.agent_ids},
+                {a: self.data[f"critic_obs/{a}"][0].copy() for a in self.agent_ids})
+
+    def step(self, action):
+        self.t += 1
+        t, d, E = self.t, self.data, self.data["E"]
+        info = {a: np.array([{} for _ in range(E)]) for a in self.agent_ids}
+        return ({a: d[f"obs/{a}"][t].copy() for a in self.agent_ids},
+                {a: d[f"critic_obs/{a}"][t].copy() for a in self.agent_ids},
+                {a: d[f"reward/{a}"][t].copy() for a in self.agent_ids},
+                {a: d[f"terminated/{a}"][t].copy() for a in self.agent_ids},
+                {a: d[f"truncated/{a}"][t].copy() for a in self.agent_ids}, info)
+
+
+def make_filter_data(seed, T, E, agents, obs_dim, critic_dim):
+    rng = np.random.default_rng(seed)
+    d = dict(agents=list(agents), E=E, T=T, obs_dim=obs_dim, critic_dim=critic_dim)
+    for i, a in enumerate(agents):
+        scale = rng.uniform(0.1, 20.0, obs_dim).astype(np.float32)
+        shift = rng.uniform(-5.0, 5.0, obs_dim).astype(np.float32)
+        d[f"obs/{a}"] = (rng.standard_normal((T + 1, E, obs_dim)).astype(np.float32) * scale + shift).astype(np.float32)
+        d[f"critic_obs/{a}"] = (rng.standard_normal((T + 1, E, critic_dim)) * 3.0 + i).astype(np.float32)
+        d[f"reward/{a}"] = (rng.standard_normal((T + 1, E)) * 4.0 + 1.0).astype(np.float32)
+        d[f"terminated/{a}"] = rng.random((T + 1, E)) < 0.08
+        d[f"truncated/{a}"] = rng.random((T + 1, E)) < 0.05
+    return d
+
+
+def gen_filters():
+    """The reference's wrapper stack in its own order (environments/wrapper_utils.py:82-112): ObservationNormalizer ->
+    ObservationClipper -> RewardNormalizer -> RewardClipper, driven for T steps over a replayed vectorised environment."""
+    from ppo_and_friends.environments.filter_wrappers import (ObservationClipper, ObservationNormalizer, RewardClipper,
+                                                                RewardNormalizer)
+    cases = {"filt_multi": dict(seed=61, T=12, E=6, agents=("a0", "a1"), obs_dim=5, critic_dim=10),
+             "filt_single": dict(seed=62, T=20, E=16, agents=("agent0",), obs_dim=24, critic_dim=24)}
+    for name, c in cases.items():
+        data = make_filter_data(**c)
+        env = ReplayEnv(data)
+        on = ObservationNormalizer(env)
+        oc = ObservationClipper(on, clip_range=(-3.0, 3.0))
+        rn = RewardNormalizer(oc, gamma=0.97)
+        rc = RewardClipper(rn, clip_range=(-2.0, 2.0))
+        out = {}
+        obs, cobs = rc.reset()
+        for a in env.agent_ids:
+            out[f"t0/obs/{a}"], out[f"t0/critic_obs/{a}"] = np.asarray(obs[a]), np.asarray(cobs[a])
+        for t in range(1, c["T"] + 1):
+            obs, cobs, rew, term, trunc, info = rc.step(None)
+            for a in env.agent_ids:
+                out[f"t{t}/obs/{a}"], out[f"t{t}/critic_obs/{a}"] = np.asarray(obs[a]), np.asarray(cobs[a])
+                out[f"t{t}/reward/{a}"] = np.asarray(rew[a])
+                out[f"t{t}/natural/{a}"] = np.array([i["natural reward"] for i in info[a]])
+        for a in env.agent_ids:
+            for tag, rs in (("actor", on.actor_running_stats[a]), ("critic", on.critic_running_stats[a]),
+                            ("reward", rn.running_stats[a])):
+                out[f"final/{tag}/{a}/mean"] = np.asarray(rs.mean, dtype=np.float64)
+                out[f"final/{tag}/{a}/variance"] = np.asarray(rs.variance, dtype=np.float64)
+                out[f"final/{tag}/{a}/count"] = np.float64(rs.count)
+            out[f"final/running_reward/{a}"] = np.asarray(rn.running_reward[a], dtype=np.float64)
+        ins = {("in_" + k): (np.array(v) if isinstance(v, list) else v) for k, v in data.items()}
+        np.savez_compressed(os.path.join(HERE, name + ".npz"), **ins, **out, hp_gamma=0.97, hp_obs_clip=np.array([-3.0, 3.0]),
+                            hp_reward_clip=np.array([-2.0, 2.0]))
+        print(name, {k: v for k, v in out.items() if k.startswith("final/reward") and k.endswith("variance")})
+
+
 if __name__ == "__main__":
     import sys
     if len(sys.argv) > 1 and sys.argv[1] == "actions":       # only the rollout-action fixtures (added later)
         gen_rollout_actions()
+    elif len(sys.argv) > 1 and sys.argv[1] == "filters":     # only the normaliser / clipper stack fixtures (round 2)
+        gen_filters()
     elif len(sys.argv) > 1 and sys.argv[1] == "shapes":      # only the BASELINE-shape update fixtures (added in round 2)
         gen_baseline_shapes()
     elif len(sys.argv) > 1 and sys.argv[1] == "edges":       # only the edge-shape segment fixtures (added later)
@@ -478,3 +563,4 @@ if __name__ == "__main__":
         gen_updates()
         gen_rollout_actions()
         gen_baseline_shapes()
+        gen_filters()
