@@ -74,19 +74,26 @@ __device__ __forceinline__ uint32_t ld_acquire_gpu(const uint32_t* p) {
 __device__ __forceinline__ void bar_stage() { asm volatile("bar.sync 1, %0;" ::"n"(kStageThreads) : "memory"); }
 
 // Grid barrier (all CTAs are co-resident: cooperative launch, one CTA per SM).  CTA b publishes `epoch` in its own
-// word; thread t of every CTA polls word t, so the release costs one L2 round trip after the last arrival and no
-// contended atomic.
+// arrival word; the threads of CTA 0 each poll one arrival word and CTA 0 then releases a single "go" word that one
+// thread of every other CTA polls: two L2 round trips after the last arrival, no contended atomic, and (unlike every CTA
+// polling every word, measured: 175 MB of L2 reads per step) almost no polling traffic competing with the operand loads.
 __device__ __forceinline__ void grid_sync(uint32_t* arrive, uint32_t epoch) {
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     __syncthreads();
-    if (threadIdx.x == 0) {
-        __threadfence();
-        st_release_gpu(arrive + kBarStride * blockIdx.x, epoch);
+    uint32_t* go = arrive + kMaxGrid * kBarStride + 4;
+    if (blockIdx.x == 0) {
+        if (threadIdx.x > 0 && threadIdx.x < gridDim.x) {
+            while (int32_t(ld_acquire_gpu(arrive + kBarStride * threadIdx.x) - epoch) < 0) {}
+        }
+        __syncthreads();
+        if (threadIdx.x == 0) st_release_gpu(go, epoch);
+    } else {
+        if (threadIdx.x == 0) {
+            st_release_gpu(arrive + kBarStride * blockIdx.x, epoch);
+            while (int32_t(ld_acquire_gpu(go) - epoch) < 0) {}
+        }
+        __syncthreads();
     }
-    if (threadIdx.x < gridDim.x) {
-        while (int32_t(ld_acquire_gpu(arrive + kBarStride * threadIdx.x) - epoch) < 0) {}
-    }
-    __syncthreads();
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
 }
 
@@ -141,11 +148,20 @@ __device__ __forceinline__ void bulk_g2s(float* smem_dst, const float* gsrc, uin
                  "l"(gsrc), "r"(bytes), "r"(smem_u32(bar))
                  : "memory");
 }
+// Executed by ALL lanes of the MMA warp with warp-uniform operands; one elected lane issues.  (Issuing from inside an
+// `if (lane == 0)` branch makes the compiler wrap every UTCHMMA in an ELECT / R2UR.BROADCAST / BRA.U.ANY waterfall, ~85 clk
+// per instruction: measured.)
 __device__ __forceinline__ void mma_tf32_ts(uint32_t tmem_d, uint32_t tmem_a, uint64_t db, uint32_t idesc, uint32_t accumulate) {
     asm volatile(
-        "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
-        "tcgen05.mma.cta_group::1.kind::tf32 [%0], [%1], %2, %3, p;\n\t}\n" ::"r"(tmem_d), "r"(tmem_a), "l"(db), "r"(idesc),
+        "{\n\t.reg .pred p, q;\n\telect.sync _|q, 0xffffffff;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+        "@q tcgen05.mma.cta_group::1.kind::tf32 [%0], [%1], %2, %3, p;\n\t}\n" ::"r"(tmem_d), "r"(tmem_a), "l"(db), "r"(idesc),
         "r"(accumulate)
+        : "memory");
+}
+__device__ __forceinline__ void umma_commit_elect(uint64_t* bar) {
+    asm volatile(
+        "{\n\t.reg .pred q;\n\telect.sync _|q, 0xffffffff;\n\t"
+        "@q tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];\n\t}\n" ::"r"(smem_u32(bar))
         : "memory");
 }
 __device__ __forceinline__ void tmem_st16(uint32_t taddr, const float (&v)[16]) {
@@ -203,7 +219,7 @@ __device__ __forceinline__ void copy_tile(float* dst, int dst_ld, const float* _
 
 template <bool A_RC, bool B_RC>
 __device__ __forceinline__ void ftile_produce(const GemmProblem& g, int tile, int64_t idx_off, float* smem, const TileBars& tb,
-                                              uint32_t& gchunk) {
+                                              uint32_t& gchunk, long long* dbg) {
     const int pt = int(threadIdx.x) - (kStageThreads + 32);
     const int bn = g.bn;
     const int m0 = (tile / g.tiles_n) * kFM, n0 = (tile % g.tiles_n) * bn;
@@ -218,6 +234,7 @@ __device__ __forceinline__ void ftile_produce(const GemmProblem& g, int tile, in
         const int s = int(gc % kFStages);
         const int k0 = c * kFK;
         if (gc >= uint32_t(kFStages)) mbar_wait(&tb.raw_free[s], (gc / kFStages - 1u) & 1u);
+        if (dbg && c < 4) dbg[2 * c] = clock64();
         float* ra = stage_raw_a(smem, s);
         float* rb = stage_raw_b(smem, s);
         if constexpr (A_RC) {      // raw A[r = tile row][k]:  A[row(m0 + r) * lda + k0 + k]
@@ -235,6 +252,7 @@ __device__ __forceinline__ void ftile_produce(const GemmProblem& g, int tile, in
             else copy_tile<false>(rb, bn, g.B, g.ldb, idxB, k0, kFK, g.K, n0, bn, g.N, pt);
         }
         cp_async_arrive(&tb.raw_full[s]);                     // one arrival per producer thread once its copies have landed
+        if (dbg && c < 4) dbg[2 * c + 1] = clock64();
     }
 }
 
@@ -274,10 +292,10 @@ __device__ __forceinline__ void ftile_mma(const GemmProblem& g, bool b_rc, float
             mma_tf32_ts(d1, a_hi + 8u * ks, b_lo + ob, idesc, first ? 0u : 1u);
             mma_tf32_ts(d2, a_lo + 8u * ks, b_hi + ob, idesc, (first && bn == 16) ? 0u : 1u);
         }
-        umma::umma_commit(&tb.mma_free[s]);
+        umma_commit_elect(&tb.mma_free[s]);
         if (dbg && c < 8) dbg[3 * c + 2] = clock64();
     }
-    umma::umma_commit(tb.acc);
+    umma_commit_elect(tb.acc);
 }
 
 // ---- converters + epilogue (warps 0..7) ----
@@ -893,7 +911,7 @@ __global__ void __launch_bounds__(kFThreads, 1) ppo_fused_step_kernel(const __gr
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     __syncthreads();
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-    const uint32_t tmem = s_tmem;
+    const uint32_t tmem = __shfl_sync(0xffffffffu, s_tmem, 0);
     const TileBars tb{s_bars, s_bars + kFStages, s_bars + 2 * kFStages, s_bars + 3 * kFStages, s_bars + 4 * kFStages};
     float* loss_smem = smem + kFStages * kStageFloatsV2;
 
@@ -906,7 +924,7 @@ __global__ void __launch_bounds__(kFThreads, 1) ppo_fused_step_kernel(const __gr
         // ============================ MMA warpgroup: warp 8 / lane 0 issues, the rest only keeps the barriers company ============================
         asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(kMmaRegs));
         uint32_t gchunk = 0;
-        const bool issuer = warp == kStageThreads / 32 && (tid & 31) == 0;
+        const bool issuer = warp == kStageThreads / 32;           // the whole warp runs the loop, one elected lane issues
         const bool producer = warp > kStageThreads / 32;          // warps 9..11
         for (int step = 0; step < P.n_steps; ++step) {
             for (int ph = 0; ph < P.n_phases; ++ph) {
@@ -917,16 +935,17 @@ __global__ void __launch_bounds__(kFThreads, 1) ppo_fused_step_kernel(const __gr
                     int pi = d.first;
                     for (int i = d.first + 1; i < d.first + d.count; ++i)
                         if (t >= P.p[i].tile_begin) pi = i;
-                    long long* mdbg = (P.stamps && blockIdx.x == 0 && t == 0 && step == P.n_steps - 1)
+                    long long* mdbg = (P.stamps && blockIdx.x == 0 && t == 0 && step == P.n_steps - 1 && (tid & 31) == 0)
                                           ? P.stamps + 3 * kMaxPhases * 4 + kMaxPhases * 32 + ph * 32 : nullptr;
+                    const bool mdbg_ok = P.stamps && blockIdx.x == 0 && t == 0 && step == P.n_steps - 1;
                     if (issuer) {
                         ftile_mma(P.p[pi], d.type == PH_FWD, smem, tb, tmem, gchunk, mdbg);
                     } else {
                         const int64_t idx_off = int64_t(cur0 + step) * P.batch_size;
                         const int tile = t - P.p[pi].tile_begin;
-                        if (d.type == PH_FWD) ftile_produce<true, true>(P.p[pi], tile, idx_off, smem, tb, gchunk);
-                        else if (d.type == PH_BWD_X) ftile_produce<true, false>(P.p[pi], tile, idx_off, smem, tb, gchunk);
-                        else ftile_produce<false, false>(P.p[pi], tile, idx_off, smem, tb, gchunk);
+                        if (d.type == PH_FWD) ftile_produce<true, true>(P.p[pi], tile, idx_off, smem, tb, gchunk, (mdbg_ok && tid == kStageThreads + 32) ? P.stamps + 3 * kMaxPhases * 4 + kMaxPhases * 32 + ph * 32 + 24 : nullptr);
+                        else if (d.type == PH_BWD_X) ftile_produce<true, false>(P.p[pi], tile, idx_off, smem, tb, gchunk, (mdbg_ok && tid == kStageThreads + 32) ? P.stamps + 3 * kMaxPhases * 4 + kMaxPhases * 32 + ph * 32 + 24 : nullptr);
+                        else ftile_produce<false, false>(P.p[pi], tile, idx_off, smem, tb, gchunk, (mdbg_ok && tid == kStageThreads + 32) ? P.stamps + 3 * kMaxPhases * 4 + kMaxPhases * 32 + ph * 32 + 24 : nullptr);
                     }
                 }
             }

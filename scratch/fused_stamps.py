@@ -59,3 +59,4 @@ for ph in range(nph):
     base = t[ph][0]
     print(f"mma thread phase {ph}: per chunk (enter wait, full ok, issued+commit) rel. to tile start:",
           [(int(r[3*c]-base), int(r[3*c+1]-base), int(r[3*c+2]-base)) for c in range(8) if r[3*c]])
+    print(f"   producer thread 0, first 4 chunks (after raw_free wait, after issue+arrive):", [(int(r[24+2*c]-base), int(r[25+2*c]-base)) for c in range(4) if r[24+2*c]])
