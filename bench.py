@@ -532,7 +532,8 @@ def main():
             }
     # live per-kernel device time of one extra (untimed) step: kernels replayed from CUDA graphs have no event of their own,
     # so their durations come from CUPTI activity records (torch.profiler); fallback: the share of the committed launch list
-    shares = kernel_shares(hp) if rank == 0 else None
+    # (single-rank runs only: the extra step is a collective operation when R > 1 and every rank would have to take it)
+    shares = kernel_shares(hp) if (rank == 0 and world == 1) else None
     gk = None
     if shares:
         gk = next((v for k, v in shares["kernels"].items() if "grouped_gemm_kernel" in k), None)
