@@ -157,9 +157,12 @@ class HotPath:
         self.w, self.ro, self.pol = w, ro, pol
         pol.initialize_dataset()
         pol.initialize_episodes(ro.E, {})
-        replay_rollout(lambda a: pol, ro)
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        replay_rollout(lambda a: pol, ro)                 # the caller side of the path: add_episode_info / end_episodes per step
         pol._ring.wait_copies()
         torch.cuda.synchronize()
+        self.record_s = time.perf_counter() - t0          # host cost of A1/A2 for the whole rollout (incl. the per-step H2D)
         self.seg = pol.dataset._seg                       # the segment table recorded by end_episodes
         self.state = PPOUpdateState({"pol": pol}, batch_size=w["B"], epochs_per_iter=w["epochs"])
         self.n = ro.T * ro.E * len(ro.agents)
@@ -529,6 +532,11 @@ def main():
                     "h2d_gbs": hp.h2d_bytes() / h2d_ms / 1e6,
                     "note": "same pass started from the pinned host ring; h2d_ms = CUDA-event time of the ring copy alone"},
             "gpu_launches": hp.launches_per_step() * args.steps,
+            "host_record": {"us_per_env_step": 1e6 * hp.record_s / (w["ts"] * w["E"]), "total_s": hp.record_s,
+                            "note": "third timer (not part of value / e2e): wall time of the caller side of the path, "
+                                    "PPOPolicy.add_episode_info + end_episodes for every step of the rollout shard, with the "
+                                    "per-step pinned-slab H2D; the reference's own figure is in cpu_baseline.sample "
+                                    "(add_episode_info caller side)"},
             }
     # live per-kernel device time of one extra (untimed) step: kernels replayed from CUDA graphs have no event of their own,
     # so their durations come from CUPTI activity records (torch.profiler); fallback: the share of the committed launch list

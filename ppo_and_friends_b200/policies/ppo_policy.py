@@ -262,27 +262,44 @@ class PPOPolicy:
         t_now = int(ring.steps[a])
         ev = _host(ending_values)
         er = _host(ending_rewards)
+        env_idxs = np.asarray(env_idxs, dtype=np.int64).reshape(-1)
+        k = env_idxs.size
+        if k == 0:
+            return
+        if not (self.have_bootstrap_clip and self.dynamic_bs_clip):
+            # every environment of the call at once (the reference loops in Python: policies/ppo_policy.py:676-712).
+            # bootstrap arrays are indexed by POSITION in env_idxs, exactly like the reference (:684-689)
+            pos = np.arange(k)
+            ending_ts = np.asarray(episode_lengths).reshape(-1)[env_idxs].astype(np.int64)
+            t0 = self._open_t0[a, env_idxs]
+            ending_value = ev[pos].astype(np.float64)
+            ending_reward = er[pos].astype(np.float64)
+            if self.have_bootstrap_clip:
+                clip = self._open_clip[a, env_idxs]
+                ending_reward = np.clip(ending_reward, clip[:, 0], clip[:, 1])              # episode_info.py:450-454
+            term = np.asarray([bool(terminal[i]) for i in range(k)]) if not isinstance(terminal, np.ndarray) \
+                else terminal.reshape(-1)[:k].astype(bool)
+            self.dataset.add_segments(a * ring.E + env_idxs, t0, t_now - t0, term, ending_value, ending_reward,
+                                      self._open_start_ts[a, env_idxs], ending_ts)
+            if self.have_bootstrap_clip:
+                self._open_clip[a, env_idxs] = self.get_bs_clip_range(None)
+            self._open_start_ts[a, env_idxs] = np.where(term, 0, ending_ts)
+            self._open_t0[a, env_idxs] = t_now
+            return
         for idx, env_i in enumerate(env_idxs):
             env_i = int(env_i)
             ending_ts = int(episode_lengths[env_i])
             t0 = int(self._open_t0[a, env_i])
             length = t_now - t0
-            # bootstrap arrays are indexed by POSITION in env_idxs, exactly like the reference
-            # (ppo_policy.py:684-689)
             ending_value = float(ev[idx])
             ending_reward = float(er[idx])
             clip = self._open_clip[a, env_i]
-            if self.have_bootstrap_clip:
-                ending_reward = float(np.clip(ending_reward, clip[0], clip[1]))   # episode_info.py:450-454
+            ending_reward = float(np.clip(ending_reward, clip[0], clip[1]))       # episode_info.py:450-454
             col = a * ring.E + env_i
             self.dataset.add_segment(col, t0, length, bool(terminal[idx]), ending_value, ending_reward,
                                      int(self._open_start_ts[a, env_i]), ending_ts)
-            if self.have_bootstrap_clip:
-                if self.dynamic_bs_clip:
-                    seg_r = ring.segment_rewards(col, t0, length)
-                    self._open_clip[a, env_i] = (float(seg_r.min()), float(seg_r.max()))
-                else:
-                    self._open_clip[a, env_i] = self.get_bs_clip_range(None)
+            seg_r = ring.segment_rewards(col, t0, length)                         # dynamic clip: this segment's reward range
+            self._open_clip[a, env_i] = (float(seg_r.min()), float(seg_r.max()))
             self._open_start_ts[a, env_i] = 0 if terminal[idx] else ending_ts
             self._open_t0[a, env_i] = t_now
 

@@ -160,6 +160,18 @@ class PPODataset(object):
         s["v_boot"].append(ending_value); s["r_boot"].append(clipped_ending_reward)
         s["start_ts"].append(starting_ts); s["end_ts"].append(ending_ts)
 
+    def add_segments(self, cols, t0s, lengths, terminals, ending_values, clipped_ending_rewards, starting_ts, ending_ts):
+        """Several segments closed by one `end_episodes` call (same meaning as add_segment, array arguments)."""
+        lengths = np.asarray(lengths)
+        if lengths.size and int(lengths.min()) < 1:
+            abort("ERROR: attempting to close an episode segment of length {}".format(int(lengths.min())))
+        s = self._seg
+        s["col"].extend(np.asarray(cols).tolist()); s["t0"].extend(np.asarray(t0s).tolist())
+        s["length"].extend(lengths.tolist()); s["terminal"].extend(np.asarray(terminals, dtype=bool).tolist())
+        s["v_boot"].extend(np.asarray(ending_values, dtype=np.float64).tolist())
+        s["r_boot"].extend(np.asarray(clipped_ending_rewards, dtype=np.float64).tolist())
+        s["start_ts"].extend(np.asarray(starting_ts).tolist()); s["end_ts"].extend(np.asarray(ending_ts).tolist())
+
     @property
     def num_segments(self):
         return len(self._seg["col"])
