@@ -50,7 +50,7 @@ static FoldPlan plan_fold(int64_t n_rows, int32_t dim, const void* p) {
     f.vec = f.width / 4;
     f.bx = (f.vec + 31) / 32 * 32;
     if (f.bx * kStatRowsPerBlock > 1024) return f;  // dim > 1024: generic path
-    const int64_t want = ceil_div64(f.rows, int64_t(kStatRowsPerBlock) * kStatUnroll * 8);
+    const int64_t want = ceil_div64(f.rows, int64_t(kStatRowsPerBlock) * kStatUnroll * (fold > 1 ? 2 : 8));
 #ifndef PPOAF_STAT_GRID_MULT_M
 #define PPOAF_STAT_GRID_MULT_M 4
 #endif
@@ -69,7 +69,9 @@ __device__ __forceinline__ void welford4(float4 x, float rn, float4& mean, float
 }
 
 // partial[(block * width + col) * 3 + {0,1,2}] = n, mean, M2
-__global__ void moments_partial_kernel(const float4* __restrict__ x, int64_t rows, int vec,
+// fold > 1 (narrow rows folded `fold` at a time into super-rows of `width` floats): the CTA also merges the fold copies of
+// every true column, so it publishes `dim` triples instead of `width` and the finalize kernel has fold x fewer to fold.
+__global__ void moments_partial_kernel(const float4* __restrict__ x, int64_t rows, int vec, int dim, int fold,
                                        double* __restrict__ partial) {
     extern __shared__ double s_part[];  // [blockDim.y][vec*4][2] mean, m2 ; counts in s_cnt
     __shared__ float s_cnt[kStatRowsPerBlock];
@@ -105,6 +107,7 @@ __global__ void moments_partial_kernel(const float4* __restrict__ x, int64_t row
     __syncthreads();
     // merge the blockDim.y row-lanes per column, fp64
     const int width = vec * 4;
+    Moments* s_fold = reinterpret_cast<Moments*>(s_part + size_t(kStatRowsPerBlock) * width * 2);   // only allocated when fold > 1
     for (int c = threadIdx.y * blockDim.x + threadIdx.x; c < width; c += blockDim.x * blockDim.y) {
         Moments acc{0.0, 0.0, 0.0};
         for (int yy = 0; yy < kStatRowsPerBlock; ++yy) {
@@ -112,29 +115,51 @@ __global__ void moments_partial_kernel(const float4* __restrict__ x, int64_t row
             Moments m{double(s_cnt[yy]), sp[0], sp[1]};
             acc = merge_moments(acc, m);
         }
-        double* out = partial + (size_t(blockIdx.x) * width + c) * 3;
-        out[0] = acc.n; out[1] = acc.mean; out[2] = acc.m2;
+        if (fold > 1) {
+            s_fold[c] = acc;                                   // width <= kMaxFoldWidth whenever fold > 1
+        } else {
+            double* out = partial + (size_t(blockIdx.x) * width + c) * 3;
+            out[0] = acc.n; out[1] = acc.mean; out[2] = acc.m2;
+        }
+    }
+    if (fold > 1) {                                            // column c = j * dim + col: tree over the fold index j
+        const int tid = threadIdx.y * blockDim.x + threadIdx.x;
+        int p2 = 1;
+        while (p2 < fold) p2 <<= 1;
+        for (int stride = p2 >> 1; stride >= 1; stride >>= 1) {
+            __syncthreads();
+            for (int c = tid; c < stride * dim; c += blockDim.x * blockDim.y) {
+                const int j = c / dim;
+                if (j + stride < fold) s_fold[c] = merge_moments(s_fold[c], s_fold[c + stride * dim]);
+            }
+        }
+        __syncthreads();
+        for (int col = tid; col < dim; col += blockDim.x * blockDim.y) {
+            double* out = partial + (size_t(blockIdx.x) * dim + col) * 3;
+            out[0] = s_fold[col].n; out[1] = s_fold[col].mean; out[2] = s_fold[col].m2;
+        }
     }
 }
 
 // One CTA per TRUE column: threads stride over the (CTA, fold) partials, then a shuffle tree merge inside
 // each warp and a fixed-order merge of the warps (Chan), so the result is deterministic.
-constexpr int kFinThreads = 128;
-__global__ void __launch_bounds__(kFinThreads)
+constexpr int kFinThreads = 128;       // wide rows: few partials per column
+constexpr int kFinThreadsMax = 1024;   // folded narrow rows (dim = 1: n_blocks x 128 partials in ONE column): one full CTA
+__global__ void __launch_bounds__(kFinThreadsMax)
 moments_finalize_kernel(const double* __restrict__ partial, int n_blocks, int width, int dim, int fold,
                         const float* __restrict__ tail_rows, int64_t tail, double* __restrict__ triple_out) {
-    __shared__ Moments s_w[kFinThreads / 32];
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    __shared__ Moments s_w[kFinThreadsMax / 32];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, n_warps = blockDim.x >> 5;
     const int col = blockIdx.x;
     Moments acc{0.0, 0.0, 0.0};
     const int items = n_blocks * fold;
-    for (int it = threadIdx.x; it < items; it += kFinThreads) {
+    for (int it = threadIdx.x; it < items; it += blockDim.x) {
         const int b = it / fold, j = it - b * fold;
         const double* p = partial + (size_t(b) * width + size_t(j) * dim + col) * 3;
         Moments m{p[0], p[1], p[2]};
         acc = merge_moments(acc, m);
     }
-    for (int64_t t = threadIdx.x; t < tail; t += kFinThreads) {
+    for (int64_t t = threadIdx.x; t < tail; t += blockDim.x) {
         Moments m{1.0, double(tail_rows[t * dim + col]), 0.0};
         acc = merge_moments(acc, m);
     }
@@ -146,12 +171,18 @@ moments_finalize_kernel(const double* __restrict__ partial, int n_blocks, int wi
     }
     if (lane == 0) s_w[warp] = acc;
     __syncthreads();
-    if (threadIdx.x == 0) {
-        Moments t = s_w[0];
-        for (int w = 1; w < kFinThreads / 32; ++w) t = merge_moments(t, s_w[w]);
-        triple_out[col] = t.mean;
-        triple_out[dim + col] = t.m2;
-        if (col == 0) triple_out[2 * dim] = t.n;
+    if (warp == 0) {                       // the warp results meet in a second fixed-order shuffle tree
+        Moments t = lane < n_warps ? s_w[lane] : Moments{0.0, 0.0, 0.0};
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            const Moments other = shfl_xor_moments(t, o);
+            t = (lane & o) ? merge_moments(other, t) : merge_moments(t, other);
+        }
+        if (lane == 0) {
+            triple_out[col] = t.mean;
+            triple_out[dim + col] = t.m2;
+            if (col == 0) triple_out[2 * dim] = t.n;
+        }
     }
 }
 
@@ -410,11 +441,13 @@ extern "C" int ppoaf_batch_moments(const float* x, int64_t n_rows, int32_t dim, 
     PPOAF_CHECK_ARG(reinterpret_cast<uintptr_t>(workspace) % 8 == 0, "ppoaf_batch_moments: workspace alignment");
     double* partial = reinterpret_cast<double*>(workspace);
     const dim3 block(f.bx, kStatRowsPerBlock);
-    const size_t smem = size_t(kStatRowsPerBlock) * f.width * 2 * sizeof(double);
-    moments_partial_kernel<<<f.grid, block, smem, s>>>(reinterpret_cast<const float4*>(x), f.rows, f.vec, partial);
+    const size_t smem = size_t(kStatRowsPerBlock) * f.width * 2 * sizeof(double) + (f.fold > 1 ? size_t(f.width) * sizeof(Moments) : 0);
+    moments_partial_kernel<<<f.grid, block, smem, s>>>(reinterpret_cast<const float4*>(x), f.rows, f.vec, dim, f.fold, partial);
     PPOAF_CHECK_LAUNCH("ppoaf_batch_moments(partial)");
-    moments_finalize_kernel<<<dim, kFinThreads, 0, s>>>(
-        partial, f.grid, f.width, dim, f.fold, x + f.rows * f.fold * int64_t(dim), f.tail, triple_out);
+    // (folded inputs arrive already merged over the fold index: one triple per CTA and true column)
+    const int fin_threads = f.grid >= 2048 ? kFinThreadsMax : kFinThreads;
+    moments_finalize_kernel<<<dim, fin_threads, 0, s>>>(
+        partial, f.grid, f.fold > 1 ? dim : f.width, dim, 1, x + f.rows * f.fold * int64_t(dim), f.tail, triple_out);
     PPOAF_CHECK_LAUNCH("ppoaf_batch_moments(finalize)");
     return 0;
 }
