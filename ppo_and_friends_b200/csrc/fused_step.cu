@@ -797,8 +797,10 @@ __device__ __forceinline__ void adam_vec4(float4& pq, const float4& gq, float4& 
         const float gk = __fmul_rn(__fmul_rn(g[k], c.inv_world), coef);
         mm[k] = __fadd_rn(mm[k], __fmul_rn(c.w1, __fsub_rn(gk, mm[k])));
         vv[k] = __fadd_rn(__fmul_rn(vv[k], c.beta2), __fmul_rn(__fmul_rn(c.w2, gk), gk));
-        const float denom = __fadd_rn(__fdiv_rn(__fsqrt_rn(vv[k]), c.bc2_sqrt), c.eps);
-        p[k] = __fadd_rn(p[k], __fdiv_rn(__fmul_rn(c.neg_step_size, mm[k]), denom));
+        float sq;                                      // approximate sqrt / divisions: same arithmetic as optim.cu (adam_vec)
+        asm("sqrt.approx.f32 %0, %1;" : "=f"(sq) : "f"(vv[k]));
+        const float denom = __fadd_rn(__fdividef(sq, c.bc2_sqrt), c.eps);
+        p[k] = __fadd_rn(p[k], __fdividef(__fmul_rn(c.neg_step_size, mm[k]), denom));
     }
     pq = make_float4(p[0], p[1], p[2], p[3]);
     mq = make_float4(mm[0], mm[1], mm[2], mm[3]);

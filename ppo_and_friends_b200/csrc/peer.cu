@@ -222,8 +222,10 @@ peer_allreduce_adam_kernel(const PeerArgs pa, float* __restrict__ params, float*
             const float gk = __fmul_rn(__fmul_rn(gg[j], inv_world), coef);
             mm[j] = __fadd_rn(mm[j], __fmul_rn(w1, __fsub_rn(gk, mm[j])));
             vv[j] = __fadd_rn(__fmul_rn(vv[j], beta2), __fmul_rn(__fmul_rn(w2, gk), gk));
-            const float denom = __fadd_rn(__fdiv_rn(__fsqrt_rn(vv[j]), bc2_sqrt), eps);
-            p[j] = __fadd_rn(p[j], __fdiv_rn(__fmul_rn(neg_step_size, mm[j]), denom));
+            float sq;                                  // approximate sqrt / divisions: same arithmetic as optim.cu (adam_vec)
+            asm("sqrt.approx.f32 %0, %1;" : "=f"(sq) : "f"(vv[j]));
+            const float denom = __fadd_rn(__fdividef(sq, bc2_sqrt), eps);
+            p[j] = __fadd_rn(p[j], __fdividef(__fmul_rn(neg_step_size, mm[j]), denom));
         }
         p4[i] = make_float4(p[0], p[1], p[2], p[3]);
         m4[i] = make_float4(mm[0], mm[1], mm[2], mm[3]);
@@ -439,8 +441,10 @@ nvls_allreduce_adam_kernel(const NvlsArgs pa, float* __restrict__ params, float*
             const float gk = __fmul_rn(__fmul_rn(gg[j], inv_world), coef);
             mm[j] = __fadd_rn(mm[j], __fmul_rn(w1, __fsub_rn(gk, mm[j])));
             vv[j] = __fadd_rn(__fmul_rn(vv[j], beta2), __fmul_rn(__fmul_rn(w2, gk), gk));
-            const float denom = __fadd_rn(__fdiv_rn(__fsqrt_rn(vv[j]), bc2_sqrt), eps);
-            p[j] = __fadd_rn(p[j], __fdiv_rn(__fmul_rn(neg_step_size, mm[j]), denom));
+            float sq;                                  // approximate sqrt / divisions: same arithmetic as optim.cu (adam_vec)
+            asm("sqrt.approx.f32 %0, %1;" : "=f"(sq) : "f"(vv[j]));
+            const float denom = __fadd_rn(__fdividef(sq, bc2_sqrt), eps);
+            p[j] = __fadd_rn(p[j], __fdividef(__fmul_rn(neg_step_size, mm[j]), denom));
         }
         m4[i] = make_float4(mm[0], mm[1], mm[2], mm[3]);
         v4[i] = make_float4(vv[0], vv[1], vv[2], vv[3]);
