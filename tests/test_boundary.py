@@ -169,3 +169,18 @@ def test_unmodified_reference_trainer_runs_on_the_b200_path(monkeypatch, continu
         ref_sd = getattr(ref.policies["single_agent"], n).state_dict()
         for k, v in getattr(pol, n).state_dict().items():
             np.testing.assert_allclose(v.cpu().numpy(), ref_sd[k].detach().numpy(), rtol=2e-3, atol=2e-5, err_msg=f"{n}/{k}")
+
+
+def test_reference_cpu_arm_runs_with_two_ranks_over_gloo():
+    """bench.py's CPU arm: the unmodified reference in two worker processes, its mpi4py calls (mpi_avg_gradients,
+    RunningMeanStd's allgather, broadcast_model_parameters) carried by gloo through the COMM_WORLD stand-in."""
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    sys.path.insert(0, root)
+    import bench
+    from oracle import ref_bench
+    w = dict(bench.WORKLOADS["c1"], ts=64, E=2, B=64, epochs=2)
+    one = ref_bench.run(w, n_ranks=1, steps=1, warmup=0, epochs_timed=1, port=29731)
+    two = ref_bench.run(w, n_ranks=2, steps=1, warmup=0, epochs_timed=1, port=29733)
+    assert one["kind"] == two["kind"] == "reference" and two["ranks"] == 2
+    assert two["threads_per_rank"] <= max(one["threads_per_rank"] // 2, 1)          # set_torch_threads: threads / num_procs
+    assert one["value"] > 0 and two["value"] > 0

@@ -108,3 +108,19 @@ def test_device_filter_stack_matches_reference(name, fused_clip):
             np.testing.assert_allclose(rs.variance, g[f"final/{tag}/{a}/variance"], rtol=1e-5)
             assert abs(rs.count - float(g[f"final/{tag}/{a}/count"])) < 1e-6
         np.testing.assert_allclose(rn.running_reward[a].cpu().numpy(), g[f"final/running_reward/{a}"], rtol=1e-12)
+
+
+@pytest.mark.gpu
+def test_two_rank_filter_stack_pools_ranks_like_the_reference():
+    """R = 2: every statistic update pools the ranks (triples exchanged instead of the reference's pickled raw batches,
+    utils/stats.py:47-53), including the reward normaliser's E sequential updates per step; against the numpy oracle
+    replaying both ranks together (tests/multi_gpu_filter_worker.py)."""
+    import os, subprocess, sys
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    port = 29400 + os.getpid() % 500
+    res = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2",
+                          "--master-addr", "127.0.0.1", "--master-port", str(port),
+                          os.path.join(root, "tests", "multi_gpu_filter_worker.py")], capture_output=True, text=True, timeout=600)
+    assert res.returncode == 0 and "MULTI_GPU_FILTER_CHECK PASS" in res.stdout, res.stdout[-3000:] + res.stderr[-3000:]
