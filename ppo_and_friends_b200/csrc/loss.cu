@@ -1,6 +1,6 @@
 // Fused PPO loss, forward + backward, for one minibatch (reference ppo.py:2299-2438 with the
 // distribution arithmetic of networks/distributions.py:491-558,694 and torch's Normal/Categorical).
-// One thread per sample; nothing but the gradients w.r.t. the two network outputs, d(log_std) and
+// One WARP per sample (each lane owns action dims l, l + 32 and 8 hidden columns); nothing but the gradients w.r.t. the two network outputs, d(log_std) and
 // six scalars ever reaches HBM.  Reductions are deterministic: per-CTA partials in fp64, summed in
 // CTA order by the last CTA to finish (self-resetting ticket).
 //

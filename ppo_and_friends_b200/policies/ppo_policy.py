@@ -361,7 +361,18 @@ class PPOPolicy:
                                        self.min_std, dist_min, dist_max, act_dim=1 if discrete else self.action_dim)
         # the reference aborts on NaN observations / predictions (:758-775); one check of the results covers both
         bad = torch.isnan(t_obs).any() | torch.isnan(action_pred).any()
-        raw_h, act_h, lp_h, bad_h = raw.cpu(), act.cpu(), lp.cpu(), bool(bad.item())
+        # ONE device->host transfer and one sync per call: the three results and the NaN flag travel as one byte buffer
+        parts = [raw.contiguous().view(torch.uint8).reshape(-1), act.contiguous().view(torch.uint8).reshape(-1),
+                 lp.contiguous().view(torch.uint8).reshape(-1), bad.to(torch.uint8).reshape(1)]
+        packed = torch.cat(parts)
+        host = self._host_out(packed.numel())
+        host.copy_(packed, non_blocking=True)
+        torch.cuda.current_stream(self.device).synchronize()
+        o0, o1, o2 = parts[0].numel(), parts[0].numel() + parts[1].numel(), packed.numel() - 1
+        raw_h = host[:o0].clone().view(raw.dtype).reshape(raw.shape)
+        act_h = host[o0:o1].clone().view(act.dtype).reshape(act.shape)
+        lp_h = host[o1:o2].clone().view(lp.dtype).reshape(lp.shape)
+        bad_h = bool(host[o2].item())
         if bad_h:
             abort("ERROR: get_rollout_actions received observations or produced action predictions "
                   "containing nan values!")
@@ -393,6 +404,14 @@ class PPOPolicy:
                                     self.min_std, self._dist_dev("min") if rescale else None,
                                     self._dist_dev("max") if rescale else None, act_dim=self.action_dim)
         return act.cpu()
+
+    def _host_out(self, n_bytes):
+        """Pinned staging buffer for the per-step device->host result transfer."""
+        buf = self.__dict__.get("_host_out_buf")
+        if buf is None or buf.numel() < n_bytes:
+            buf = torch.empty(max(n_bytes, 4096), dtype=torch.uint8, pin_memory=True)
+            self._host_out_buf = buf
+        return buf[:n_bytes]
 
     def _dist_dev(self, which):
         """The Gaussian head's output range as device tensors (built once)."""
