@@ -20,6 +20,7 @@
 #include "umma.cuh"
 #include "loss_common.cuh"
 #include <stdlib.h>
+#include <cuda.h>          // CUtensorMap types only: cuTensorMapEncodeTiled is fetched through cudaGetDriverEntryPoint
 
 namespace ppoaf {
 namespace fused {
@@ -45,6 +46,10 @@ enum { PH_FWD = 0, PH_BWD_X, PH_BWD_W, PH_LOSS, PH_ADAM };
 struct PhaseDesc { int type, first, count, n_tiles; };
 
 struct FusedPlan {
+    // TMA descriptors of the operands that are plain (un-gathered, 16-byte friendly) matrices: one 2-D box per tile and
+    // K chunk (problem flavour bit 4: A through TMA, bit 5: B through TMA); everything else is staged with cp.async
+    alignas(64) CUtensorMap tmA[kMaxProblems];
+    alignas(64) CUtensorMap tmB[kMaxProblems];
     int n_phases, n_problems, n_steps, batch;
     int loss_finalize_phase;               // phase at whose start the last CTA folds the loss partials
     int batch_size;                        // cursor stride of the permutation
@@ -59,6 +64,9 @@ struct FusedPlan {
     const double* hp;
     int64_t* adam_step;
     int32_t* mb_cursor;
+    // gathered minibatch rows, double-buffered by step parity: xg[net] is [2 * batch_size][xg_ld[net]] floats
+    float* xg[2]; const float* x_src[2]; int x_dim[2]; int xg_ld[2];
+    const int64_t* perm; int64_t n_flat;
     long long* stamps;                     // debug (PPOAF_FUSED_STAMPS=1): clock64 per phase of the last step, CTAs 0 / mid / last
     uint32_t* bar;                         // [0 .. grid*kBarStride): arrival words; [kMaxGrid*kBarStride]: epoch of the last launch
 };
@@ -127,13 +135,15 @@ __device__ __forceinline__ float4 ldcg4(const float* __restrict__ p, int n_valid
 // Operands that are not 16-byte friendly (ld or extent not a multiple of 4 floats: first layers of 18 / 54 inputs, the
 // head gradients) skip the raw tile: the converters read them from global memory directly.
 // =========================================================================================================
-constexpr int kRawLdA = 36;                                   // floats per raw K-major row (144 B: conflict-free LDS.128 per lane)
-constexpr int kRawAFloats = kFM * kRawLdA;                    // 18432 B (MN-major raw A: 32 x 128 floats = 16 KB fits)
-constexpr int kRawBFloats = 1280;                             // 5120 B >= 32 x 36 floats; keeps the UMMA B tiles 1024-byte aligned
+constexpr int kRawLdA = 32;                                   // raw K-major rows are dense (128 B) with their 16-byte chunks XOR-swizzled by
+                                                              // (row & 7): the layout TMA SWIZZLE_128B writes, conflict-free for the
+                                                              // converters' one-row-per-lane LDS.128
+constexpr int kRawAFloats = kFM * kRawLdA;                    // 16 KB (MN-major raw A: 32 x 128 floats, unswizzled)
+constexpr int kRawBFloats = kMaxBN * kRawLdA;                 // 4 KB  (MN-major raw B: 32 x bn floats)
 constexpr int kOpBFloats = kMaxBN * kFK;                      // one UMMA B tile (hi or lo)
 constexpr int kStageFloatsV2 = kRawAFloats + kRawBFloats + 2 * kOpBFloats;
 constexpr int kParts = 4;                                     // accumulator pairs
-static_assert(kRawBFloats >= kMaxBN * kRawLdA && ((kRawAFloats + kRawBFloats) * 4) % 1024 == 0 && (kStageFloatsV2 * 4) % 1024 == 0, "stage layout");
+static_assert((kRawAFloats * 4) % 1024 == 0 && ((kRawAFloats + kRawBFloats) * 4) % 1024 == 0 && (kStageFloatsV2 * 4) % 1024 == 0, "stage layout");
 constexpr size_t kFusedSmemBytes = (size_t(kFStages) * kStageFloatsV2 + kLossSmemFloats) * sizeof(float) + 1024;
 constexpr int kTmemA = 0, kTmemAcc = 256;                     // TMEM columns: A stages 4 x (32 hi | 32 lo), accumulators 8 x 32
 
@@ -164,6 +174,13 @@ __device__ __forceinline__ void umma_commit_elect(uint64_t* bar) {
         "@q tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];\n\t}\n" ::"r"(smem_u32(bar))
         : "memory");
 }
+// tf32 round-to-nearest (ties away) with integer arithmetic: add half an ulp of the 10-bit mantissa, clear the 13 low bits.
+// Same result as cvt.rna.tf32.f32 for finite normal inputs, but IADD + LOP run at 64 lanes/clk/SM whereas the conversion
+// unit runs at 16: with cvt the split was ~600 of the ~1100 clk a converter warp spends per K chunk (measured).
+__device__ __forceinline__ float tf32_round(float x) {
+    return __uint_as_float((__float_as_uint(x) + 0x1000u) & 0xFFFFE000u);
+}
+
 __device__ __forceinline__ void tmem_st16(uint32_t taddr, const float (&v)[16]) {
     asm volatile(
         "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16};\n" ::"r"(taddr),
@@ -193,82 +210,126 @@ __device__ __forceinline__ bool b_is_raw(const GemmProblem& g) { return (g.flavo
 // ---- producers (warps 9..11, 96 threads): cp.async of both operand tiles of a chunk into the raw stage ----
 // 16-byte copies when the operand is 16-byte friendly (flavour bits), 4-byte copies otherwise; rows / columns beyond the
 // operand's extent are zero-filled (src-size 0), so the raw tiles are always fully defined.
-constexpr int kProdThreads = 96;
-template <bool VEC>
+constexpr int kProdThreads = 128;          // warps 8..11: each produces (cp.async / TMA) AND issues one k-step's MMAs
+constexpr int kLook = kFStages - 1;        // chunks the producer side runs ahead of the MMA side inside a tile
+// KROWS: the tile rows are reduction indices (MN-major raw tile): rows beyond the extent must be ZERO (they are multiplied into
+// valid outputs) while columns beyond the extent only feed outputs that are never stored and are skipped; K-major tiles
+// (KROWS = false) the other way round.  row_add: address-only row offset (odd-step half of a double-buffered operand).
+template <bool VEC, bool SWZ, bool KROWS>
 __device__ __forceinline__ void copy_tile(float* dst, int dst_ld, const float* __restrict__ P, int ld, const int64_t* __restrict__ idx,
-                                          int row0, int n_rows, int row_ext, int col0, int n_cols, int col_ext, int pt) {
+                                          int row0, int n_rows, int row_ext, int col0, int n_cols, int col_ext, int row_add, int pt) {
+    const int nr = KROWS ? n_rows : min(n_rows, row_ext - row0);
+    int nc = KROWS ? min(n_cols, col_ext - col0) : n_cols;
+    if (nr <= 0 || nc <= 0) return;
     if constexpr (VEC) {
-        const int cpr = n_cols >> 2;                          // 16-byte chunks per row (a power of two)
+        int cpr = 1;                                          // 16-byte chunks per row, rounded up to a power of two
+        while (cpr * 4 < nc) cpr <<= 1;
         const int sh = 31 - __clz(cpr);
-        for (int op = pt; op < n_rows * cpr; op += kProdThreads) {
+        for (int op = pt; op < nr * cpr; op += kProdThreads) {
             const int r = op >> sh, c4 = op & (cpr - 1);
             const bool ok = row0 + r < row_ext && col0 + 4 * c4 < col_ext;
-            const int64_t gr = ok ? (idx ? idx[row0 + r] : int64_t(row0 + r)) : 0;
-            cp_async_16(dst + r * dst_ld + 4 * c4, P + gr * ld + (ok ? col0 + 4 * c4 : 0), ok);
+            const int64_t gr = ok ? (idx ? idx[row0 + r] : int64_t(row0 + r + row_add)) : 0;
+            const int pc = SWZ ? (c4 ^ (r & 7)) : c4;
+            cp_async_16(dst + r * dst_ld + 4 * pc, P + gr * ld + (ok ? col0 + 4 * c4 : 0), ok);
         }
     } else {
-        const int sh = 31 - __clz(n_cols);
-        for (int op = pt; op < n_rows * n_cols; op += kProdThreads) {
-            const int r = op >> sh, c = op & (n_cols - 1);
+        int ncp = 1;
+        while (ncp < nc) ncp <<= 1;
+        const int sh = 31 - __clz(ncp);
+        for (int op = pt; op < nr * ncp; op += kProdThreads) {
+            const int r = op >> sh, c = op & (ncp - 1);
             const bool ok = row0 + r < row_ext && col0 + c < col_ext;
-            const int64_t gr = ok ? (idx ? idx[row0 + r] : int64_t(row0 + r)) : 0;
-            cp_async_4(dst + r * dst_ld + c, P + gr * ld + (ok ? col0 + c : 0), ok);
+            const int64_t gr = ok ? (idx ? idx[row0 + r] : int64_t(row0 + r + row_add)) : 0;
+            const int pc = SWZ ? ((((c >> 2) ^ (r & 7)) << 2) | (c & 3)) : c;
+            cp_async_4(dst + r * dst_ld + pc, P + gr * ld + (ok ? col0 + c : 0), ok);
         }
     }
 }
 
+__device__ __forceinline__ void mbar_expect_tx_only(uint64_t* bar, uint32_t bytes) {
+    asm volatile("mbarrier.expect_tx.relaxed.cta.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void tma_load_2d(float* smem_dst, const CUtensorMap* tm, int c0, int c1, uint64_t* bar) {
+    asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];" ::"r"(
+                     smem_u32(smem_dst)),
+                 "l"(reinterpret_cast<uint64_t>(tm)), "r"(c0), "r"(c1), "r"(smem_u32(bar))
+                 : "memory");
+}
+
+// One K chunk of both operand tiles -> raw stage (executed by the 128 threads of the MMA warpgroup).
 template <bool A_RC, bool B_RC>
-__device__ __forceinline__ void ftile_produce(const GemmProblem& g, int tile, int64_t idx_off, float* smem, const TileBars& tb,
-                                              uint32_t& gchunk, long long* dbg) {
-    const int pt = int(threadIdx.x) - (kStageThreads + 32);
+__device__ __forceinline__ void produce_chunk(const GemmProblem& g, const CUtensorMap* tmA, const CUtensorMap* tmB, int m0, int n0,
+                                              const int64_t* idxA, const int64_t* idxB, int addA, int addB, int c, uint32_t gc,
+                                              float* smem, const TileBars& tb) {
+    const int pt = int(threadIdx.x) - kStageThreads;
+    const int bn = g.bn;
+    const bool vecA = (g.flavour & 2) != 0, vecB = (g.flavour & 1) != 0;
+    const bool tmaA = (g.flavour & 16) != 0, tmaB = (g.flavour & 32) != 0;
+    const uint32_t tma_bytes = (tmaA ? uint32_t(kFM * kFK * 4) : 0u) + (tmaB ? uint32_t(bn * kFK * 4) : 0u);   // whole boxes (OOB = zeros)
+    const int s = int(gc % kFStages);
+    const int k0 = c * kFK;
+    if (gc >= uint32_t(kFStages)) mbar_wait(&tb.raw_free[s], (gc / kFStages - 1u) & 1u);
+    float* ra = stage_raw_a(smem, s);
+    float* rb = stage_raw_b(smem, s);
+    if (pt == 0 && tma_bytes) {
+        // one TMA box per operand: K-major {k0, row0} -> [rows][32] swizzled; MN-major {out0, k0} -> [32][outs]
+        mbar_expect_tx_only(&tb.raw_full[s], tma_bytes);
+        if (tmaA) { if constexpr (A_RC) tma_load_2d(ra, tmA, k0, m0 + addA, &tb.raw_full[s]); else tma_load_2d(ra, tmA, m0, k0 + addA, &tb.raw_full[s]); }
+        if (tmaB) { if constexpr (B_RC) tma_load_2d(rb, tmB, k0, n0 + addB, &tb.raw_full[s]); else tma_load_2d(rb, tmB, n0, k0 + addB, &tb.raw_full[s]); }
+    }
+    if (!tmaA) {
+        if constexpr (A_RC) {      // raw A[r = tile row][k]:  A[row(m0 + r) * lda + k0 + k]
+            if (vecA) copy_tile<true, true, false>(ra, kRawLdA, g.A, g.lda, idxA, m0, kFM, g.M, k0, kFK, g.K, addA, pt);
+            else copy_tile<false, true, false>(ra, kRawLdA, g.A, g.lda, idxA, m0, kFM, g.M, k0, kFK, g.K, addA, pt);
+        } else {                   // raw A[k][m = tile row]:  A[row(k0 + k) * lda + m0 + m]
+            if (vecA) copy_tile<true, false, true>(ra, kFM, g.A, g.lda, idxA, k0, kFK, g.K, m0, kFM, g.M, addA, pt);
+            else copy_tile<false, false, true>(ra, kFM, g.A, g.lda, idxA, k0, kFK, g.K, m0, kFM, g.M, addA, pt);
+        }
+    }
+    if (!tmaB) {
+        if constexpr (B_RC) {
+            if (vecB) copy_tile<true, true, false>(rb, kRawLdA, g.B, g.ldb, idxB, n0, bn, g.N, k0, kFK, g.K, addB, pt);
+            else copy_tile<false, true, false>(rb, kRawLdA, g.B, g.ldb, idxB, n0, bn, g.N, k0, kFK, g.K, addB, pt);
+        } else {
+            if (vecB) copy_tile<true, false, true>(rb, bn, g.B, g.ldb, idxB, k0, kFK, g.K, n0, bn, g.N, addB, pt);
+            else copy_tile<false, false, true>(rb, bn, g.B, g.ldb, idxB, k0, kFK, g.K, n0, bn, g.N, addB, pt);
+        }
+    }
+    cp_async_arrive(&tb.raw_full[s]);                     // one arrival per thread once its copies (if any) have landed
+}
+
+// ---- MMA warpgroup (warps 8..11): producer AND issuer ----
+// A tcgen05.mma costs ~80-100 clk of issue whatever its shape (measured), so the four k-steps of a chunk are split over the
+// four warps (`ks` = warp - 8: disjoint accumulators, every warp commits to the stage / accumulator barriers).  The same
+// warps feed the pipeline: before issuing chunk c they put chunk c + kLook in flight (TMA box loads by one thread, cp.async
+// by all 128 for operands TMA cannot describe), so the loads run kLook chunks ahead of the MMAs inside a tile.
+template <bool A_RC, bool B_RC>
+__device__ __forceinline__ void ftile_mma(const GemmProblem& g, const CUtensorMap* tmA, const CUtensorMap* tmB, int tile,
+                                          int64_t idx_off, int odd, uint32_t ks, float* smem, const TileBars& tb, uint32_t tmem,
+                                          uint32_t& gchunk, long long* dbg) {
     const int bn = g.bn;
     const int m0 = (tile / g.tiles_n) * kFM, n0 = (tile % g.tiles_n) * bn;
     const int n_chunks = (g.K + kFK - 1) / kFK;
     const uint32_t c0 = gchunk;
     gchunk += uint32_t(n_chunks);
-    const bool vecA = (g.flavour & 2) != 0, vecB = (g.flavour & 1) != 0;
     const int64_t* idxA = g.idxA ? g.idxA + idx_off : nullptr;
     const int64_t* idxB = g.idxB ? g.idxB + idx_off : nullptr;
-    for (int c = 0; c < n_chunks; ++c) {
-        const uint32_t gc = c0 + uint32_t(c);
-        const int s = int(gc % kFStages);
-        const int k0 = c * kFK;
-        if (gc >= uint32_t(kFStages)) mbar_wait(&tb.raw_free[s], (gc / kFStages - 1u) & 1u);
-        if (dbg && c < 4) dbg[2 * c] = clock64();
-        float* ra = stage_raw_a(smem, s);
-        float* rb = stage_raw_b(smem, s);
-        if constexpr (A_RC) {      // raw A[r = tile row][k]:  A[row(m0 + r) * lda + k0 + k]
-            if (vecA) copy_tile<true>(ra, kRawLdA, g.A, g.lda, idxA, m0, kFM, g.M, k0, kFK, g.K, pt);
-            else copy_tile<false>(ra, kRawLdA, g.A, g.lda, idxA, m0, kFM, g.M, k0, kFK, g.K, pt);
-        } else {                   // raw A[k][m = tile row]:  A[row(k0 + k) * lda + m0 + m]
-            if (vecA) copy_tile<true>(ra, kFM, g.A, g.lda, idxA, k0, kFK, g.K, m0, kFM, g.M, pt);
-            else copy_tile<false>(ra, kFM, g.A, g.lda, idxA, k0, kFK, g.K, m0, kFM, g.M, pt);
-        }
-        if constexpr (B_RC) {
-            if (vecB) copy_tile<true>(rb, kRawLdA, g.B, g.ldb, idxB, n0, bn, g.N, k0, kFK, g.K, pt);
-            else copy_tile<false>(rb, kRawLdA, g.B, g.ldb, idxB, n0, bn, g.N, k0, kFK, g.K, pt);
-        } else {
-            if (vecB) copy_tile<true>(rb, bn, g.B, g.ldb, idxB, k0, kFK, g.K, n0, bn, g.N, pt);
-            else copy_tile<false>(rb, bn, g.B, g.ldb, idxB, k0, kFK, g.K, n0, bn, g.N, pt);
-        }
-        cp_async_arrive(&tb.raw_full[s]);                     // one arrival per producer thread once its copies have landed
-        if (dbg && c < 4) dbg[2 * c + 1] = clock64();
-    }
-}
-
-// ---- MMA issuer (warp 8, one lane) ----
-__device__ __forceinline__ void ftile_mma(const GemmProblem& g, bool b_rc, float* smem, const TileBars& tb, uint32_t tmem,
-                                          uint32_t& gchunk, long long* dbg) {
-    const int bn = g.bn;
-    const int n_chunks = (g.K + kFK - 1) / kFK;
-    const uint32_t c0 = gchunk;
-    gchunk += uint32_t(n_chunks);
+    const int addA = odd ? g.a_par : 0, addB = odd ? g.b_par : 0;
     // A comes from TMEM (K-major by construction); B from shared memory
-    const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((b_rc ? 0u : 1u) << 16) | (uint32_t(bn >> 3) << 17) |
+    const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((B_RC ? 0u : 1u) << 16) | (uint32_t(bn >> 3) << 17) |
                            (uint32_t(kFM >> 4) << 24);
-    const uint64_t db0 = b_rc ? umma::desc_base<true>() : umma::desc_base<false>();
-    const uint64_t ub = b_rc ? umma::kstep_units<true>() : umma::kstep_units<false>();
+    const uint64_t db0 = umma::desc_base<B_RC>();
+    const uint64_t ob = ks * umma::kstep_units<B_RC>();
+    uint32_t d0, d1, d2;
+    // every (k-step, term) owns its accumulator, so consecutive MMAs are independent
+    // (12 slots of 16 columns; at bn = 32 the two small terms of a k-step share one: 8 slots of 32 columns)
+    if (bn == 16) { d0 = tmem + uint32_t(kTmemAcc) + (ks * 3u) * 16u; d1 = d0 + 16u; d2 = d0 + 32u; }
+    else { d0 = tmem + uint32_t(kTmemAcc) + (ks * 2u) * 32u; d1 = d0 + 32u; d2 = d1; }
+    for (int c = 0; c < kLook && c < n_chunks; ++c)
+        produce_chunk<A_RC, B_RC>(g, tmA, tmB, m0, n0, idxA, idxB, addA, addB, c, c0 + uint32_t(c), smem, tb);
     for (int c = 0; c < n_chunks; ++c) {
+        if (c + kLook < n_chunks)
+            produce_chunk<A_RC, B_RC>(g, tmA, tmB, m0, n0, idxA, idxB, addA, addB, c + kLook, c0 + uint32_t(c + kLook), smem, tb);
         const uint32_t gc = c0 + uint32_t(c);
         const int s = int(gc % kFStages);
         if (dbg && c < 8) dbg[3 * c] = clock64();
@@ -279,19 +340,10 @@ __device__ __forceinline__ void ftile_mma(const GemmProblem& g, bool b_rc, float
         const uint64_t b_hi = db0 | uint64_t((sb >> 4) & 0x3FFF);
         const uint64_t b_lo = db0 | uint64_t(((sb + kOpBFloats * 4) >> 4) & 0x3FFF);
         const uint32_t a_hi = tmem + uint32_t(kTmemA + s * 64), a_lo = a_hi + 32u;
-        // every (k-step, term) owns its accumulator, so consecutive MMAs are independent and the tensor pipe overlaps them
-        // (12 slots of 16 columns; at bn = 32 the two small terms of a k-step share one: 8 slots of 32 columns)
         const bool first = c == 0;                            // first chunk: overwrite
-#pragma unroll
-        for (uint32_t ks = 0; ks < kFK / 8; ++ks) {
-            const uint64_t ob = ks * ub;
-            uint32_t d0, d1, d2;
-            if (bn == 16) { d0 = tmem + uint32_t(kTmemAcc) + (ks * 3u) * 16u; d1 = d0 + 16u; d2 = d0 + 32u; }
-            else { d0 = tmem + uint32_t(kTmemAcc) + (ks * 2u) * 32u; d1 = d0 + 32u; d2 = d1; }
-            mma_tf32_ts(d0, a_hi + 8u * ks, b_hi + ob, idesc, first ? 0u : 1u);
-            mma_tf32_ts(d1, a_hi + 8u * ks, b_lo + ob, idesc, first ? 0u : 1u);
-            mma_tf32_ts(d2, a_lo + 8u * ks, b_hi + ob, idesc, (first && bn == 16) ? 0u : 1u);
-        }
+        mma_tf32_ts(d0, a_hi + 8u * ks, b_hi + ob, idesc, first ? 0u : 1u);
+        mma_tf32_ts(d1, a_hi + 8u * ks, b_lo + ob, idesc, first ? 0u : 1u);
+        mma_tf32_ts(d2, a_lo + 8u * ks, b_hi + ob, idesc, (first && bn == 16) ? 0u : 1u);
         umma_commit_elect(&tb.mma_free[s]);
         if (dbg && c < 8) dbg[3 * c + 2] = clock64();
     }
@@ -359,7 +411,7 @@ __device__ __forceinline__ void ftile(const GemmProblem& g, int tile, int64_t id
             if constexpr (A_RC) {
 #pragma unroll
                 for (int i = 0; i < 4; ++i) {
-                    const float4 v = *reinterpret_cast<const float4*>(ra + ml * kRawLdA + 16 * h + 4 * i);
+                    const float4 v = *reinterpret_cast<const float4*>(ra + ml * kRawLdA + (((4 * h + i) ^ (ml & 7)) << 2));
                     x[4 * i] = v.x; x[4 * i + 1] = v.y; x[4 * i + 2] = v.z; x[4 * i + 3] = v.w;
                 }
             } else {
@@ -369,29 +421,32 @@ __device__ __forceinline__ void ftile(const GemmProblem& g, int tile, int64_t id
         }
         if (b_active) {
             const float* rb = stage_raw_b(smem, s);
-            if constexpr (B_RC) bq = *reinterpret_cast<const float4*>(rb + b_r * kRawLdA + 4 * b_g);
+            if constexpr (B_RC) bq = *reinterpret_cast<const float4*>(rb + b_r * kRawLdA + ((b_g ^ (b_r & 7)) << 2));
             else bq = *reinterpret_cast<const float4*>(rb + b_r * bn + 4 * b_g);
         }
         // the raw tile may be refilled as soon as every warp has read it
         __syncwarp();
         if (lane == 0) mbar_arrive(&tb.raw_free[s]);
+        if (dbg && c == 3) dbg[29] = clock64();
 
         float hi[16], lo[16];
 #pragma unroll
         for (int i = 0; i < 16; ++i) {
-            hi[i] = tf32_rna(x[i]);
-            lo[i] = tf32_rna(x[i] - hi[i]);
+            hi[i] = tf32_round(x[i]);
+            lo[i] = tf32_round(x[i] - hi[i]);
             if constexpr (EPI == EPI_BWD_W) rowsum += x[i];
         }
         float4 bh, bl;
-        bh.x = tf32_rna(bq.x); bl.x = tf32_rna(bq.x - bh.x);
-        bh.y = tf32_rna(bq.y); bl.y = tf32_rna(bq.y - bh.y);
-        bh.z = tf32_rna(bq.z); bl.z = tf32_rna(bq.z - bh.z);
-        bh.w = tf32_rna(bq.w); bl.w = tf32_rna(bq.w - bh.w);
+        bh.x = tf32_round(bq.x); bl.x = tf32_round(bq.x - bh.x);
+        bh.y = tf32_round(bq.y); bl.y = tf32_round(bq.y - bh.y);
+        bh.z = tf32_round(bq.z); bl.z = tf32_round(bq.z - bh.z);
+        bh.w = tf32_round(bq.w); bl.w = tf32_round(bq.w - bh.w);
 
         // the MMAs of chunk gc - kFStages have finished reading this stage's TMEM columns and B tiles
+        if (dbg && c == 3) dbg[30] = clock64();
         if (gc >= uint32_t(kFStages)) mbar_wait(&tb.mma_free[s], (gc / kFStages - 1u) & 1u);
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        if (dbg && c == 3) dbg[31] = clock64();
         const uint32_t ta = tmem + (uint32_t(q * 32) << 16) + uint32_t(kTmemA + s * 64 + 16 * h);
         tmem_st16(ta, hi);
         tmem_st16(ta + 32u, lo);
@@ -401,7 +456,9 @@ __device__ __forceinline__ void ftile(const GemmProblem& g, int tile, int64_t id
             *reinterpret_cast<float4*>(ob + kOpBFloats + b_dst) = bl;
         }
         asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+        if (dbg && c == 3) dbg[26] = clock64();
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy stores -> visible to the tensor core
+        if (dbg && c == 3) dbg[27] = clock64();
         asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
         __syncwarp();
         if (lane == 0) mbar_arrive(&tb.op_full[s]);
@@ -636,7 +693,7 @@ __device__ __forceinline__ void loss_phase(const LossArgs& a, int cur, float* s_
         float bad_value = isnan(v) ? 1.f : 0.f;
 
         const float* pred = s_pred + warp * kFusedPredLd;
-        float* dpred = a.d_actor_out + int64_t(i) * a.pred_dim;
+        float* dpred = a.d_actor_out + int64_t(i) * (a.d_actor_ld ? a.d_actor_ld : a.pred_dim);
         float* sdp = s_dpred + warp * kFusedPredLd;
         actor_head_loss<true>(a, gaussian, true, gl, j, pred, dpred, sdp, s_sd, adv, lp_old, inv_b, w_ent, clip_lo, clip_hi, sc,
                               dsd, bad_value);
@@ -646,7 +703,7 @@ __device__ __forceinline__ void loss_phase(const LossArgs& a, int cur, float* s_
         float dv1 = 0.f;
         sc[LS_CRITIC] = critic_term(v, target, a.use_huber, dv1);
         if (gl != 0) sc[LS_CRITIC] = 0.f;
-        if (gl == 0) a.d_critic_out[i] = dv1 * inv_b;
+        if (gl == 0) a.d_critic_out[int64_t(i) * (a.d_critic_ld ? a.d_critic_ld : 1)] = dv1 * inv_b;
         const float bad_any = group_max(bad_value);
         sc[LS_BAD_VALUE] = gl == 0 ? bad_any : 0.f;
 
@@ -882,6 +939,34 @@ __device__ __forceinline__ void adam_phase(const FusedPlan& P, double p1, double
     if (dbg) dbg[6] = clock64();
 }
 
+// Rows of minibatch `mb` (perm[mb * B + r]) of both observation arrays -> the contiguous half `odd` of xg: the first-layer
+// GEMMs (forward and dW) then read a plain matrix through TMA instead of gathering 16 bytes at a time.  Rows beyond the
+// minibatch's extent are zero-filled (they are reduction rows of the first-layer dW).  All converter threads of all CTAs.
+__device__ __forceinline__ void gather_minibatch(const FusedPlan& P, int mb, int odd) {
+    const int B = P.batch_size;
+    const int64_t first = int64_t(mb) * B;
+    const int64_t left = P.n_flat - first;
+    const int rows = int(left < 0 ? 0 : (left < B ? left : B));
+    const int tid = threadIdx.x;
+    for (int r = int(blockIdx.x); r < B; r += int(gridDim.x)) {
+        const int64_t j = r < rows ? P.perm[first + r] : -1;
+#pragma unroll
+        for (int k = 0; k < 2; ++k) {
+            const int D = P.x_dim[k], ld = P.xg_ld[k];
+            float* dst = P.xg[k] + (size_t(odd) * B + r) * ld;
+            const float* src = P.x_src[k] + (j < 0 ? 0 : j) * D;
+            if ((D & 3) == 0 && (reinterpret_cast<uintptr_t>(P.x_src[k]) & 15) == 0) {
+                for (int c = tid; c < D / 4; c += kStageThreads) {
+                    const float4 v = j >= 0 ? ldg_stream_f4(reinterpret_cast<const float4*>(src) + c) : make_float4(0.f, 0.f, 0.f, 0.f);
+                    reinterpret_cast<float4*>(dst)[c] = v;
+                }
+            } else {
+                for (int c = tid; c < ld; c += kStageThreads) dst[c] = (j >= 0 && c < D) ? src[c] : 0.f;
+            }
+        }
+    }
+}
+
 __global__ void __launch_bounds__(kFThreads, 1) ppo_fused_step_kernel(const __grid_constant__ FusedPlan P) {
     extern __shared__ uint8_t smem_raw[];
     __shared__ __align__(8) uint64_t s_bars[4 * kFStages + 1];
@@ -902,12 +987,12 @@ __global__ void __launch_bounds__(kFThreads, 1) ppo_fused_step_kernel(const __gr
     if (tid == 32) {
 #pragma unroll
         for (int i = 0; i < kFStages; ++i) {
-            mbar_init(&s_bars[i], kProdThreads);                   // raw_full: one cp.async arrival per producer thread
+            mbar_init(&s_bars[i], kProdThreads);                   // raw_full: one cp.async arrival per thread of the MMA warpgroup
             mbar_init(&s_bars[kFStages + i], kStageThreads / 32);  // raw_free: one arrival per converter warp
             mbar_init(&s_bars[2 * kFStages + i], kStageThreads / 32);   // op_full
-            mbar_init(&s_bars[3 * kFStages + i], 1);               // mma_free: tcgen05.commit
+            mbar_init(&s_bars[3 * kFStages + i], 4);               // mma_free: one tcgen05.commit per issuer warp
         }
-        mbar_init(&s_bars[4 * kFStages], 1);                       // accumulators complete
+        mbar_init(&s_bars[4 * kFStages], 4);                       // accumulators complete (all four issuers)
         asm volatile("fence.mbarrier_init.release.cluster;");
     }
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
@@ -926,29 +1011,24 @@ __global__ void __launch_bounds__(kFThreads, 1) ppo_fused_step_kernel(const __gr
         // ============================ MMA warpgroup: warp 8 / lane 0 issues, the rest only keeps the barriers company ============================
         asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(kMmaRegs));
         uint32_t gchunk = 0;
-        const bool issuer = warp == kStageThreads / 32;           // the whole warp runs the loop, one elected lane issues
-        const bool producer = warp > kStageThreads / 32;          // warps 9..11
+        const uint32_t ks = uint32_t(warp - kStageThreads / 32);   // this warp's k-step of every chunk
         for (int step = 0; step < P.n_steps; ++step) {
+            const int64_t idx_off = int64_t(cur0 + step) * P.batch_size;
             for (int ph = 0; ph < P.n_phases; ++ph) {
-                if (step > 0 || ph > 0) grid_sync(P.bar, ++epoch);
+                grid_sync(P.bar, ++epoch);                        // (before the very first phase: the gathered rows of step 0)
                 const PhaseDesc d = P.ph[ph];
-                if (d.type == PH_LOSS || d.type == PH_ADAM || !(issuer || producer)) continue;
+                if (d.type == PH_LOSS || d.type == PH_ADAM) continue;
+                if (tid == kStageThreads) asm volatile("fence.proxy.async;" ::: "memory");   // other CTAs' generic-proxy writes -> TMA reads
                 for (int t = int(blockIdx.x); t < d.n_tiles; t += int(gridDim.x)) {
                     int pi = d.first;
                     for (int i = d.first + 1; i < d.first + d.count; ++i)
                         if (t >= P.p[i].tile_begin) pi = i;
-                    long long* mdbg = (P.stamps && blockIdx.x == 0 && t == 0 && step == P.n_steps - 1 && (tid & 31) == 0)
+                    long long* mdbg = (P.stamps && blockIdx.x == 0 && t == 0 && step == P.n_steps - 1 && tid == kStageThreads)
                                           ? P.stamps + 3 * kMaxPhases * 4 + kMaxPhases * 32 + ph * 32 : nullptr;
-                    const bool mdbg_ok = P.stamps && blockIdx.x == 0 && t == 0 && step == P.n_steps - 1;
-                    if (issuer) {
-                        ftile_mma(P.p[pi], d.type == PH_FWD, smem, tb, tmem, gchunk, mdbg);
-                    } else {
-                        const int64_t idx_off = int64_t(cur0 + step) * P.batch_size;
-                        const int tile = t - P.p[pi].tile_begin;
-                        if (d.type == PH_FWD) ftile_produce<true, true>(P.p[pi], tile, idx_off, smem, tb, gchunk, (mdbg_ok && tid == kStageThreads + 32) ? P.stamps + 3 * kMaxPhases * 4 + kMaxPhases * 32 + ph * 32 + 24 : nullptr);
-                        else if (d.type == PH_BWD_X) ftile_produce<true, false>(P.p[pi], tile, idx_off, smem, tb, gchunk, (mdbg_ok && tid == kStageThreads + 32) ? P.stamps + 3 * kMaxPhases * 4 + kMaxPhases * 32 + ph * 32 + 24 : nullptr);
-                        else ftile_produce<false, false>(P.p[pi], tile, idx_off, smem, tb, gchunk, (mdbg_ok && tid == kStageThreads + 32) ? P.stamps + 3 * kMaxPhases * 4 + kMaxPhases * 32 + ph * 32 + 24 : nullptr);
-                    }
+                    const int tile = t - P.p[pi].tile_begin;
+                    if (d.type == PH_FWD) ftile_mma<true, true>(P.p[pi], &P.tmA[pi], &P.tmB[pi], tile, idx_off, step & 1, ks, smem, tb, tmem, gchunk, mdbg);
+                    else if (d.type == PH_BWD_X) ftile_mma<true, false>(P.p[pi], &P.tmA[pi], &P.tmB[pi], tile, idx_off, step & 1, ks, smem, tb, tmem, gchunk, mdbg);
+                    else ftile_mma<false, false>(P.p[pi], &P.tmA[pi], &P.tmB[pi], tile, idx_off, step & 1, ks, smem, tb, tmem, gchunk, mdbg);
                 }
             }
         }
@@ -959,6 +1039,7 @@ __global__ void __launch_bounds__(kFThreads, 1) ppo_fused_step_kernel(const __gr
         const double b1d = P.hp[PPOAF_HP_BETA1], b2d = P.hp[PPOAF_HP_BETA2];
         if (tid == 0) { p1 = pow(b1d, double(t0)); p2 = pow(b2d, double(t0)); }
         uint32_t gchunk = 0, gtile = 0;
+        gather_minibatch(P, cur0, 0);                                  // step 0's rows; later steps are gathered in the LOSS phase
         for (int step = 0; step < P.n_steps; ++step) {
             const int cur = cur0 + step;
             const int64_t idx_off = int64_t(cur) * P.batch_size;
@@ -970,12 +1051,13 @@ __global__ void __launch_bounds__(kFThreads, 1) ppo_fused_step_kernel(const __gr
                     if (slot >= 0) stp = P.stamps + (slot * kMaxPhases + ph) * 4;
                 }
                 if (stp) stp[0] = clock64();
-                if (step > 0 || ph > 0) grid_sync(P.bar, ++epoch);
+                grid_sync(P.bar, ++epoch);
                 if (stp) stp[1] = clock64();
                 const PhaseDesc d = P.ph[ph];
                 if (ph == P.loss_finalize_phase && blockIdx.x == gridDim.x - 1) loss_finalize(P.loss, s_dsd, s_red, s_tot, s_sq);
                 if (d.type == PH_LOSS) {
                     loss_phase(P.loss, cur, loss_smem, s_sd, s_dsd, s_red, (stp && blockIdx.x == 0) ? P.stamps + 3 * kMaxPhases * 4 + ph * 32 : nullptr);
+                    if (step + 1 < P.n_steps) gather_minibatch(P, cur + 1, (step + 1) & 1);   // read again 4 barriers from now
                 } else if (d.type == PH_ADAM) {
                     adam_phase(P, p1, p2, s_scr, s_f, (stp && blockIdx.x == 0) ? P.stamps + 3 * kMaxPhases * 4 + ph * 32 : nullptr);
                 } else {
@@ -1022,6 +1104,8 @@ struct FScratch {
     double* loss_partials;
     float* act[2][PPOAF_MAX_LAYERS + 1];
     float* dz[2][PPOAF_MAX_LAYERS + 1];
+    float* xg[2];                 // gathered minibatch rows, [2 * max_batch][xg_ld]
+    int xg_ld[2];
     size_t total;
 };
 
@@ -1050,8 +1134,12 @@ static void fcarve(const ppoaf_update_cfg* cfg, int max_batch, char* base, FScra
     for (int k = 0; k < 2; ++k)
         for (int l = 1; l <= nets[k]->n_layers; ++l) {
             out->act[k][l] = reinterpret_cast<float*>(take(size_t(max_batch) * nets[k]->dims[l] * sizeof(float)));
-            out->dz[k][l] = reinterpret_cast<float*>(take(size_t(max_batch) * nets[k]->dims[l] * sizeof(float)));
+            out->dz[k][l] = reinterpret_cast<float*>(take(size_t(max_batch) * ((nets[k]->dims[l] + 3) / 4 * 4) * sizeof(float)));
         }
+    for (int k = 0; k < 2; ++k) {
+        out->xg_ld[k] = (nets[k]->dims[0] + 3) / 4 * 4;          // 16-byte row pitch: TMA-able whatever the observation width
+        out->xg[k] = reinterpret_cast<float*>(take(size_t(2) * max_batch * out->xg_ld[k] * sizeof(float)));
+    }
     out->total = off;
 }
 
@@ -1065,6 +1153,43 @@ static const char* unsupported_reason(const ppoaf_update_cfg* cfg) {
     if (cfg->act_dim > kMaxAct || cfg->actor.dims[La] > kMaxAct) return "action width out of range";
     if (cfg->world_size > 1) return "multi-rank exchange runs through the launch-chain path";
     return nullptr;
+}
+
+// ---- TMA descriptors (driver entry point fetched at run time: the library links cudart only) ----
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+static EncodeTiledFn encode_tiled_fn() {
+    static EncodeTiledFn fn = nullptr;
+    static bool tried = false;
+    if (!tried) {
+        tried = true;
+        const char* e = getenv("PPOAF_FUSED_TMA");
+        if (e && e[0] == '0') return nullptr;                     // PPOAF_FUSED_TMA=0: cp.async for every operand
+        void* p = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
+            q == cudaDriverEntryPointSuccess)
+            fn = reinterpret_cast<EncodeTiledFn>(p);
+        else
+            (void)cudaGetLastError();
+    }
+    return fn;
+}
+// matrix [n_rows x n_cols] fp32, row stride ld floats; box = box_cols (contiguous) x box_rows; K-major raw tiles take the
+// 128-byte swizzle (box_cols = 32), MN-major raw tiles are plain
+static bool make_tmap(CUtensorMap* tm, const float* base, int64_t n_rows, int64_t n_cols, int64_t ld, int box_cols, int box_rows,
+                      bool swizzle128) {
+    EncodeTiledFn fn = encode_tiled_fn();
+    if (!fn || reinterpret_cast<uintptr_t>(base) % 16 != 0 || (ld * 4) % 16 != 0 || box_cols > 256 || box_rows > 256) return false;
+    const cuuint64_t gdim[2] = {cuuint64_t(n_cols), cuuint64_t(n_rows)};
+    const cuuint64_t gstride[1] = {cuuint64_t(ld) * 4};
+    const cuuint32_t box[2] = {cuuint32_t(box_cols), cuuint32_t(box_rows)};
+    const cuuint32_t estr[2] = {1, 1};
+    const CUresult r = fn(tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(base), gdim, gstride, box, estr,
+                          CU_TENSOR_MAP_INTERLEAVE_NONE, swizzle128 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_NONE,
+                          CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    return r == CUDA_SUCCESS;
 }
 
 static inline bool vec4_ok(const float* p, int ld, int contig_extent) {
@@ -1106,6 +1231,21 @@ static int build_plan(const ppoaf_update_cfg* cfg, const ppoaf_update_bufs* b, i
     auto begin_phase = [&](int type) { P->ph[nph].type = type; P->ph[nph].first = np; P->ph[nph].count = 0; P->ph[nph].n_tiles = 0; };
     auto add_problem = [&](GemmProblem& g, int bn) {
         g.bn = bn;
+        // operands that are plain 16-byte-friendly matrices travel through TMA (no gather: a tensor map cannot indirect)
+        const int epi = g.flavour >> 2;
+        const bool a_rc = epi != EPI_BWD_W, b_rc = epi == EPI_FWD;
+        if (!g.idxA) {
+            // K-major A: matrix [M x K] (ld = lda), box 32 x 128;  MN-major A (dZ as [K x M]): box 128 x 32.  An operand
+            // that alternates between two halves by step parity is described as ONE matrix of both halves (a_par rows apart)
+            const bool ok = a_rc ? make_tmap(&P->tmA[np], g.A, g.M + g.a_par, g.K, g.lda, kFK, kFM, true)
+                                 : make_tmap(&P->tmA[np], g.A, g.K + g.a_par, g.M, g.lda, kFM, kFK, false);
+            if (ok) g.flavour |= 16;
+        }
+        if (!g.idxB) {
+            const bool ok = b_rc ? make_tmap(&P->tmB[np], g.B, g.N + g.b_par, g.K, g.ldb, kFK, bn, true)
+                                 : make_tmap(&P->tmB[np], g.B, g.K + g.b_par, g.N, g.ldb, bn, kFK, false);
+            if (ok) g.flavour |= 32;
+        }
         g.tiles_n = ceil_div(g.N, bn);
         g.tile_begin = P->ph[nph].n_tiles;
         P->ph[nph].n_tiles += g.tiles_n * ceil_div(g.M, kFM);
@@ -1120,15 +1260,16 @@ static int build_plan(const ppoaf_update_cfg* cfg, const ppoaf_update_bufs* b, i
         const int bn = pick_bn(grid, 16, MN, 2);
         for (int k = 0; k < 2; ++k) {
             GemmProblem g{};
-            const float* X = l == 0 ? x0[k] : sc.act[k][l];
+            const float* X = l == 0 ? sc.xg[k] : sc.act[k][l];
             const int in = net[k]->dims[l], out = net[k]->dims[l + 1];
+            const int ldx = l == 0 ? sc.xg_ld[k] : in;
             const float* W = par[k] + off[k][2 * l];
-            g.A = X; g.lda = in; g.B = W; g.ldb = in; g.C = sc.act[k][l + 1]; g.ldc = out;
+            g.A = X; g.lda = ldx; g.B = W; g.ldb = in; g.C = sc.act[k][l + 1]; g.ldc = out;
             g.M = rows; g.N = out; g.K = in;
-            g.idxA = l == 0 ? b->perm : nullptr;
+            g.a_par = l == 0 ? b->batch_size : 0;
             g.bias = par[k] + off[k][2 * l + 1];
             g.act = net[k]->activation;
-            g.flavour = EPI_FWD * 4 + (vec4_ok(X, in, in) ? 2 : 0) + (vec4_ok(W, in, in) ? 1 : 0);
+            g.flavour = EPI_FWD * 4 + (vec4_ok(X, ldx, in) ? 2 : 0) + (vec4_ok(W, in, in) ? 1 : 0);
             add_problem(g, bn);
         }
         ++nph;
@@ -1168,13 +1309,15 @@ static int build_plan(const ppoaf_update_cfg* cfg, const ppoaf_update_bufs* b, i
             for (int l = L - 1; l >= 0; --l) {             // widest-K problems (none here: K = rows for all) / top layers first
                 GemmProblem g{};
                 const int in = net[k]->dims[l], out = net[k]->dims[l + 1];
-                const float* X = l == 0 ? x0[k] : sc.act[k][l];
-                g.A = sc.dz[k][l + 1]; g.lda = out; g.B = X; g.ldb = in; g.C = grd[k] + off[k][2 * l]; g.ldc = in;
+                const float* X = l == 0 ? sc.xg[k] : sc.act[k][l];
+                const int ldx = l == 0 ? sc.xg_ld[k] : in;
+                const int lddz = l == L - 1 ? (out + 3) / 4 * 4 : out;      // the head gradients are stored with a 16-byte row pitch
+                g.A = sc.dz[k][l + 1]; g.lda = lddz; g.B = X; g.ldb = ldx; g.C = grd[k] + off[k][2 * l]; g.ldc = in;
                 g.M = out; g.N = in; g.K = rows;
-                g.idxB = l == 0 ? b->perm : nullptr;
+                g.b_par = l == 0 ? b->batch_size : 0;
                 g.dbias = grd[k] + off[k][2 * l + 1];
                 g.sq_out = sq[k] + used[k];
-                g.flavour = EPI_BWD_W * 4 + (vec4_ok(g.A, out, out) ? 2 : 0) + (vec4_ok(X, in, in) ? 1 : 0);
+                g.flavour = EPI_BWD_W * 4 + (vec4_ok(g.A, lddz, out) ? 2 : 0) + (vec4_ok(X, ldx, in) ? 1 : 0);
                 used[k] += ceil_div(out, kFM) * ceil_div(in, bn);
                 add_problem(g, bn);
             }
@@ -1205,6 +1348,8 @@ static int build_plan(const ppoaf_update_cfg* cfg, const ppoaf_update_bufs* b, i
     a.epoch_stats = b->epoch_stats;
     a.d_actor_out = sc.dz[0][L];
     a.d_critic_out = sc.dz[1][L];
+    a.d_actor_ld = (cfg->actor.dims[L] + 3) / 4 * 4;
+    a.d_critic_ld = 4;
     a.d_log_std = gaussian ? grd[0] + off[0][2 * L] : nullptr;
     a.sq_log_std = sc.sq_actor + (P->n_sq_a - 1);
     a.partials = reinterpret_cast<float*>(sc.loss_partials);
@@ -1216,8 +1361,8 @@ static int build_plan(const ppoaf_update_cfg* cfg, const ppoaf_update_bufs* b, i
     a.normalize_values = cfg->normalize_values;
     a.vf_clip_enabled = 0;
     a.min_std = cfg->min_std;
-    a.pf_rows[0] = b->obs;
-    a.pf_rows[1] = b->critic_obs;
+    a.pf_rows[0] = nullptr;                 // the next minibatch's rows are GATHERED during the LOSS phase instead of prefetched
+    a.pf_rows[1] = nullptr;
     a.pf_row_bytes[0] = cfg->actor.dims[0] * int(sizeof(float));
     a.pf_row_bytes[1] = cfg->critic.dims[0] * int(sizeof(float));
     a.n_flat = b->n_flat;
@@ -1235,6 +1380,11 @@ static int build_plan(const ppoaf_update_cfg* cfg, const ppoaf_update_bufs* b, i
     a.Hc = cfg->critic.dims[L - 1];
     a.act = cfg->actor.activation;
 
+    for (int k = 0; k < 2; ++k) {
+        P->xg[k] = sc.xg[k]; P->xg_ld[k] = sc.xg_ld[k]; P->x_src[k] = x0[k]; P->x_dim[k] = net[k]->dims[0];
+    }
+    P->perm = b->perm;
+    P->n_flat = b->n_flat;
     P->mirror.n = 0;
     P->params = b->params; P->grads = b->grads; P->m = b->adam_m; P->v = b->adam_v;
     P->n_actor = n_actor; P->n_total = n_actor + n_critic;

@@ -83,6 +83,9 @@ struct LossArgs {
     const void* pf_rows[2];
     int pf_row_bytes[2];
     int64_t n_flat;
+    // fused_step.cu: row pitch of d_actor_out / d_critic_out (0: dense, pred_dim / 1) - padded to 16 bytes there so that the
+    // head layers' dW operand is a TMA-able matrix
+    int d_actor_ld, d_critic_ld;
 };
 bool loss_head_fusable(int pred_dim, int Ha, int Hc, int vf_clip_enabled);
 size_t loss_workspace_bytes(int max_batch, int act_dim);

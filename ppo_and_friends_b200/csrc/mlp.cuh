@@ -65,7 +65,8 @@ struct GemmProblem {
     int tile_begin;                 // first linear tile id of this problem inside the launch
     int b_static;                   // B is not written by the launch right before this one (and has no gather): it may
                                     //   be staged before the programmatic-dependency wait
-    int bn;                         // fused_step.cu: tile width along N chosen for this problem's phase (16 / 32 / 64)
+    int bn;                         // fused_step.cu: tile width along N chosen for this problem's phase (16 / 32)
+    int a_par, b_par;               // fused_step.cu: operand rows to skip on odd steps (double-buffered gathered minibatch rows)
 };
 struct MirrorSet {                   // peer copies of the gradient buffer (R > 1 push exchange): byte offsets from
     int n;                           //   a local gradient address to the same element in every peer's receive slot
