@@ -88,20 +88,16 @@ __device__ __forceinline__ void bar_stage() { asm volatile("bar.sync 1, %0;" ::"
 __device__ __forceinline__ void grid_sync(uint32_t* arrive, uint32_t epoch) {
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     __syncthreads();
-    uint32_t* go = arrive + kMaxGrid * kBarStride + 4;
-    if (blockIdx.x == 0) {
-        if (threadIdx.x > 0 && threadIdx.x < gridDim.x) {
-            while (int32_t(ld_acquire_gpu(arrive + kBarStride * threadIdx.x) - epoch) < 0) {}
-        }
-        __syncthreads();
-        if (threadIdx.x == 0) st_release_gpu(go, epoch);
-    } else {
-        if (threadIdx.x == 0) {
-            st_release_gpu(arrive + kBarStride * blockIdx.x, epoch);
-            while (int32_t(ld_acquire_gpu(go) - epoch) < 0) {}
-        }
-        __syncthreads();
+    if (threadIdx.x == 0) {
+        // flat counter: every CTA adds one and polls the same word until it reads epoch * grid (the grid size is the same
+        // for every launch on a workspace, so the count carries over from launch to launch like the epoch does).  One L2
+        // round trip shorter than an arrival word per CTA gathered by CTA 0 + a release word (measured: 5.5K -> 2.5K clk)
+        uint32_t* cnt = arrive + kMaxGrid * kBarStride + 4;
+        const uint32_t target = epoch * gridDim.x;
+        asm volatile("red.release.gpu.global.add.u32 [%0], 1;" ::"l"(cnt) : "memory");
+        while (int32_t(ld_acquire_gpu(cnt) - target) < 0) {}
     }
+    __syncthreads();
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
 }
 
@@ -141,10 +137,14 @@ constexpr int kRawLdA = 32;                                   // raw K-major row
 constexpr int kRawAFloats = kFM * kRawLdA;                    // 16 KB (MN-major raw A: 32 x 128 floats, unswizzled)
 constexpr int kRawBFloats = kMaxBN * kRawLdA;                 // 4 KB  (MN-major raw B: 32 x bn floats)
 constexpr int kOpBFloats = kMaxBN * kFK;                      // one UMMA B tile (hi or lo)
-constexpr int kStageFloatsV2 = kRawAFloats + kRawBFloats + 2 * kOpBFloats;
+constexpr int kRawStages = 6;                                  // raw (TMA / cp.async) ring: deeper than the operand ring, the L2 -> shared
+                                                              // memory latency under 148 CTAs' load is ~2.4K clk (measured), several chunks
+constexpr int kRawStageFloats = kRawAFloats + kRawBFloats;    // 20 KB
+constexpr int kOpStageFloats = 2 * kOpBFloats;                // B hi | lo in the UMMA layout (A hi | lo live in TMEM), kFStages of them
 constexpr int kParts = 4;                                     // accumulator pairs
-static_assert((kRawAFloats * 4) % 1024 == 0 && ((kRawAFloats + kRawBFloats) * 4) % 1024 == 0 && (kStageFloatsV2 * 4) % 1024 == 0, "stage layout");
-constexpr size_t kFusedSmemBytes = (size_t(kFStages) * kStageFloatsV2 + kLossSmemFloats) * sizeof(float) + 1024;
+static_assert((kRawAFloats * 4) % 1024 == 0 && (kRawStageFloats * 4) % 1024 == 0 && (kOpStageFloats * 4) % 1024 == 0, "stage layout");
+constexpr int kTileSmemFloats = kRawStages * kRawStageFloats + kFStages * kOpStageFloats;
+constexpr size_t kFusedSmemBytes = (size_t(kTileSmemFloats) + kLossSmemFloats) * sizeof(float) + 1024;
 constexpr int kTmemA = 0, kTmemAcc = 256;                     // TMEM columns: A stages 4 x (32 hi | 32 lo), accumulators 8 x 32
 
 __device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
@@ -196,12 +196,12 @@ __device__ __forceinline__ void tmem_ld8(uint32_t taddr, uint32_t (&r)[8]) {
                  : "r"(taddr));
 }
 
-struct TileBars {            // all [kFStages] except acc
+struct TileBars {            // raw_*: [kRawStages]; op_full / mma_free: [kFStages]
     uint64_t* raw_full; uint64_t* raw_free; uint64_t* op_full; uint64_t* mma_free; uint64_t* acc;
 };
-__device__ __forceinline__ float* stage_raw_a(float* smem, int s) { return smem + s * kStageFloatsV2; }
-__device__ __forceinline__ float* stage_raw_b(float* smem, int s) { return smem + s * kStageFloatsV2 + kRawAFloats; }
-__device__ __forceinline__ float* stage_op_b(float* smem, int s) { return smem + s * kStageFloatsV2 + kRawAFloats + kRawBFloats; }
+__device__ __forceinline__ float* stage_raw_a(float* smem, int sr) { return smem + sr * kRawStageFloats; }
+__device__ __forceinline__ float* stage_raw_b(float* smem, int sr) { return smem + sr * kRawStageFloats + kRawAFloats; }
+__device__ __forceinline__ float* stage_op_b(float* smem, int s) { return smem + kRawStages * kRawStageFloats + s * kOpStageFloats; }
 
 // whether an operand travels through a raw tile (TMA bulk copies need 16-byte aligned rows and sizes)
 __device__ __forceinline__ bool a_is_raw(const GemmProblem& g) { return (g.flavour & 2) != 0; }
@@ -211,7 +211,7 @@ __device__ __forceinline__ bool b_is_raw(const GemmProblem& g) { return (g.flavo
 // 16-byte copies when the operand is 16-byte friendly (flavour bits), 4-byte copies otherwise; rows / columns beyond the
 // operand's extent are zero-filled (src-size 0), so the raw tiles are always fully defined.
 constexpr int kProdThreads = 128;          // warps 8..11: each produces (cp.async / TMA) AND issues one k-step's MMAs
-constexpr int kLook = kFStages - 1;        // chunks the producer side runs ahead of the MMA side inside a tile
+constexpr int kLook = kRawStages - 1;        // chunks the producer side runs ahead of the MMA side inside a tile
 // KROWS: the tile rows are reduction indices (MN-major raw tile): rows beyond the extent must be ZERO (they are multiplied into
 // valid outputs) while columns beyond the extent only feed outputs that are never stored and are skipped; K-major tiles
 // (KROWS = false) the other way round.  row_add: address-only row offset (odd-step half of a double-buffered operand).
@@ -266,9 +266,9 @@ __device__ __forceinline__ void produce_chunk(const GemmProblem& g, const CUtens
     const bool vecA = (g.flavour & 2) != 0, vecB = (g.flavour & 1) != 0;
     const bool tmaA = (g.flavour & 16) != 0, tmaB = (g.flavour & 32) != 0;
     const uint32_t tma_bytes = (tmaA ? uint32_t(kFM * kFK * 4) : 0u) + (tmaB ? uint32_t(bn * kFK * 4) : 0u);   // whole boxes (OOB = zeros)
-    const int s = int(gc % kFStages);
+    const int s = int(gc % kRawStages);
     const int k0 = c * kFK;
-    if (gc >= uint32_t(kFStages)) mbar_wait(&tb.raw_free[s], (gc / kFStages - 1u) & 1u);
+    if (gc >= uint32_t(kRawStages)) mbar_wait(&tb.raw_free[s], (gc / kRawStages - 1u) & 1u);
     float* ra = stage_raw_a(smem, s);
     float* rb = stage_raw_b(smem, s);
     if (pt == 0 && tma_bytes) {
@@ -367,14 +367,24 @@ __device__ __forceinline__ void ftile(const GemmProblem& g, int tile, int64_t id
     const int ml = q * 32 + lane;                             // this thread's tile row (= TMEM lane)
     const int m = m0 + ml;
 
-    // B element group of this thread: 4 consecutive floats of the contiguous direction
-    const int gpr = B_RC ? 8 : (bn >> 2);                     // groups per raw row
-    const int b_r = tid / gpr, b_g = tid % gpr;               // K-major: (row n, k quad);  MN-major: (k row, output quad)
-    const bool b_active = B_RC ? (b_r < bn) : (b_r < kFK);
-    int b_dst = 0;
-    if (b_active) {
-        if constexpr (B_RC) b_dst = b_r * 32 + ((b_g ^ (b_r & 7)) * 4);
-        else b_dst = (b_g / 8) * 1024 + (b_r / 4) * 128 + (b_r % 4) * 32 + ((((b_g / 2) % 4) ^ (b_r % 4)) * 8) + (b_g % 2) * 4;
+    // The converters work as two groups of four warps (one warp per TMEM lane quarter): group `h` takes the chunks whose
+    // global index has parity h, so the two groups' wait -> LDS -> split -> tcgen05.st -> fence -> arrive chains overlap.
+    // B quads of this thread: 4 consecutive floats of the contiguous direction, bn * 8 quads per chunk over 128 threads
+    const int gt = tid & 127;
+    const int gpr = B_RC ? 8 : (bn >> 2);                     // quads per raw row
+    const int n_bq = bn * 8;
+    int b_src[2], b_dst[2];
+#pragma unroll
+    for (int j = 0; j < 2; ++j) {
+        const int t = gt + 128 * j;
+        const int b_r = t / gpr, b_g = t % gpr;               // K-major: (row n, k quad);  MN-major: (k row, output quad)
+        if constexpr (B_RC) {
+            b_src[j] = b_r * kRawLdA + ((b_g ^ (b_r & 7)) << 2);
+            b_dst[j] = b_r * 32 + ((b_g ^ (b_r & 7)) * 4);
+        } else {
+            b_src[j] = b_r * bn + 4 * b_g;
+            b_dst[j] = (b_g / 8) * 1024 + (b_r / 4) * 128 + (b_r % 4) * 32 + ((((b_g / 2) % 4) ^ (b_r % 4)) * 8) + (b_g % 2) * 4;
+        }
     }
     float rowsum = 0.f;                                       // EPI_BWD_W: bias gradient = sum over k of this thread's A row
 
@@ -399,66 +409,78 @@ __device__ __forceinline__ void ftile(const GemmProblem& g, int tile, int64_t id
     if (dbg) dbg[1] = clock64();
 
 #pragma unroll 1
-    for (int c = 0; c < n_chunks; ++c) {
+    for (int c = int((c0 ^ uint32_t(h)) & 1u); c < n_chunks; c += 2) {
         const uint32_t gc = c0 + uint32_t(c);
-        const int s = int(gc % kFStages);
-        float x[16];
-        float4 bq = make_float4(0.f, 0.f, 0.f, 0.f);
-        mbar_wait(&tb.raw_full[s], (gc / kFStages) & 1u);
+        const int s = int(gc % kFStages), sr = int(gc % kRawStages);
+        float x[32];
+        float4 bq[2];
+        bq[0] = bq[1] = make_float4(0.f, 0.f, 0.f, 0.f);
+        mbar_wait(&tb.raw_full[sr], (gc / kRawStages) & 1u);
         if (dbg && c < 12) dbg[4 + 2 * c] = clock64();
         {
-            const float* ra = stage_raw_a(smem, s);
+            const float* ra = stage_raw_a(smem, sr);
             if constexpr (A_RC) {
 #pragma unroll
-                for (int i = 0; i < 4; ++i) {
-                    const float4 v = *reinterpret_cast<const float4*>(ra + ml * kRawLdA + (((4 * h + i) ^ (ml & 7)) << 2));
+                for (int i = 0; i < 8; ++i) {
+                    const float4 v = *reinterpret_cast<const float4*>(ra + ml * kRawLdA + ((i ^ (ml & 7)) << 2));
                     x[4 * i] = v.x; x[4 * i + 1] = v.y; x[4 * i + 2] = v.z; x[4 * i + 3] = v.w;
                 }
             } else {
 #pragma unroll
-                for (int i = 0; i < 16; ++i) x[i] = ra[(16 * h + i) * kFM + ml];
+                for (int i = 0; i < 32; ++i) x[i] = ra[i * kFM + ml];
             }
         }
-        if (b_active) {
-            const float* rb = stage_raw_b(smem, s);
-            if constexpr (B_RC) bq = *reinterpret_cast<const float4*>(rb + b_r * kRawLdA + ((b_g ^ (b_r & 7)) << 2));
-            else bq = *reinterpret_cast<const float4*>(rb + b_r * bn + 4 * b_g);
-        }
-        // the raw tile may be refilled as soon as every warp has read it
-        __syncwarp();
-        if (lane == 0) mbar_arrive(&tb.raw_free[s]);
-        if (dbg && c == 3) dbg[29] = clock64();
-
-        float hi[16], lo[16];
+        {
+            const float* rb = stage_raw_b(smem, sr);
 #pragma unroll
-        for (int i = 0; i < 16; ++i) {
-            hi[i] = tf32_round(x[i]);
-            lo[i] = tf32_round(x[i] - hi[i]);
-            if constexpr (EPI == EPI_BWD_W) rowsum += x[i];
+            for (int j = 0; j < 2; ++j)
+                if (gt + 128 * j < n_bq) bq[j] = *reinterpret_cast<const float4*>(rb + b_src[j]);
         }
-        float4 bh, bl;
-        bh.x = tf32_round(bq.x); bl.x = tf32_round(bq.x - bh.x);
-        bh.y = tf32_round(bq.y); bl.y = tf32_round(bq.y - bh.y);
-        bh.z = tf32_round(bq.z); bl.z = tf32_round(bq.z - bh.z);
-        bh.w = tf32_round(bq.w); bl.w = tf32_round(bq.w - bh.w);
+        // the raw tile may be refilled as soon as every warp of the group has read it
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&tb.raw_free[sr]);
+        if (dbg && c == 4) dbg[29] = clock64();
 
+        float4 bh[2], bl[2];
+#pragma unroll
+        for (int j = 0; j < 2; ++j) {
+            bh[j].x = tf32_round(bq[j].x); bl[j].x = tf32_round(bq[j].x - bh[j].x);
+            bh[j].y = tf32_round(bq[j].y); bl[j].y = tf32_round(bq[j].y - bh[j].y);
+            bh[j].z = tf32_round(bq[j].z); bl[j].z = tf32_round(bq[j].z - bh[j].z);
+            bh[j].w = tf32_round(bq[j].w); bl[j].w = tf32_round(bq[j].w - bh[j].w);
+        }
         // the MMAs of chunk gc - kFStages have finished reading this stage's TMEM columns and B tiles
-        if (dbg && c == 3) dbg[30] = clock64();
+        if (dbg && c == 4) dbg[30] = clock64();
         if (gc >= uint32_t(kFStages)) mbar_wait(&tb.mma_free[s], (gc / kFStages - 1u) & 1u);
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-        if (dbg && c == 3) dbg[31] = clock64();
-        const uint32_t ta = tmem + (uint32_t(q * 32) << 16) + uint32_t(kTmemA + s * 64 + 16 * h);
-        tmem_st16(ta, hi);
-        tmem_st16(ta + 32u, lo);
-        if (b_active) {
+        if (dbg && c == 4) dbg[31] = clock64();
+        const uint32_t ta = tmem + (uint32_t(q * 32) << 16) + uint32_t(kTmemA + s * 64);
+#pragma unroll
+        for (int kh = 0; kh < 2; ++kh) {
+            float hi[16], lo[16];
+#pragma unroll
+            for (int i = 0; i < 16; ++i) {
+                const float v = x[16 * kh + i];
+                hi[i] = tf32_round(v);
+                lo[i] = tf32_round(v - hi[i]);
+                if constexpr (EPI == EPI_BWD_W) rowsum += v;
+            }
+            tmem_st16(ta + uint32_t(16 * kh), hi);
+            tmem_st16(ta + 32u + uint32_t(16 * kh), lo);
+        }
+        {
             float* ob = stage_op_b(smem, s);
-            *reinterpret_cast<float4*>(ob + b_dst) = bh;
-            *reinterpret_cast<float4*>(ob + kOpBFloats + b_dst) = bl;
+#pragma unroll
+            for (int j = 0; j < 2; ++j)
+                if (gt + 128 * j < n_bq) {
+                    *reinterpret_cast<float4*>(ob + b_dst[j]) = bh[j];
+                    *reinterpret_cast<float4*>(ob + kOpBFloats + b_dst[j]) = bl[j];
+                }
         }
         asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
-        if (dbg && c == 3) dbg[26] = clock64();
+        if (dbg && c == 4) dbg[26] = clock64();
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy stores -> visible to the tensor core
-        if (dbg && c == 3) dbg[27] = clock64();
+        if (dbg && c == 4) dbg[27] = clock64();
         asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
         __syncwarp();
         if (lane == 0) mbar_arrive(&tb.op_full[s]);
@@ -482,17 +504,26 @@ __device__ __forceinline__ void ftile(const GemmProblem& g, int tile, int64_t id
 #pragma unroll
         for (int j = 0; j < 8; ++j) v8[j] = 0.f;
         const uint32_t tcol = tmem + (uint32_t(q * 32) << 16) + uint32_t(kTmemAcc + h * half + j8);
+        // every accumulator slot in flight at once (one TMEM round trip instead of twelve), then the sums in a fixed
+        // order: small-term accumulators first, the big ones last
+        uint32_t r[12][8];
 #pragma unroll
-        for (int pass = 0; pass < 2; ++pass) {      // pass 0: small-term accumulators, pass 1: big-term accumulators
+        for (int sl = 0; sl < 12; ++sl) {
+            if (sl < n_slots) tmem_ld8(tcol + uint32_t(sl * bn), r[sl]);
+            else {
+#pragma unroll
+                for (int j = 0; j < 8; ++j) r[sl][j] = 0u;
+            }
+        }
+        asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+        for (int pass = 0; pass < 2; ++pass) {
 #pragma unroll
             for (int sl = 0; sl < 12; ++sl) {
                 const bool small = bn == 16 ? (sl % 3 != 0) : (sl % 2 == 1);
-                if (sl < n_slots && small == (pass == 0)) {
-                    uint32_t r[8];
-                    tmem_ld8(tcol + uint32_t(sl * bn), r);
-                    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+                if (small == (pass == 0)) {
 #pragma unroll
-                    for (int j = 0; j < 8; ++j) v8[j] += __uint_as_float(r[j]);
+                    for (int j = 0; j < 8; ++j) v8[j] += __uint_as_float(r[sl][j]);
                 }
             }
         }
@@ -530,7 +561,7 @@ __device__ __forceinline__ void ftile(const GemmProblem& g, int tile, int64_t id
     if (dbg) dbg[28] = clock64();
 
     if constexpr (EPI == EPI_BWD_W) {
-        // bias gradient: this thread summed its row over the k's of its half; the two halves meet in shared memory
+        // bias gradient: this thread summed its row over the chunks of its group; the two groups meet in shared memory
         __shared__ float s_rowsum[2][kFM];
         s_rowsum[h][ml] = rowsum;
         const double w = warp_sum(double(sq));
@@ -556,6 +587,39 @@ __device__ __forceinline__ void ftile(const GemmProblem& g, int tile, int64_t id
     }
 }
 
+// Head weights of both networks -> shared memory.  They were written by the ADAM phase of the previous step (several grid
+// barriers ago), so the staging warps run this BEFORE the grid barrier that opens the LOSS phase: the L2 loads overlap the
+// wait for the slowest CTA of the last hidden layer.
+__device__ __forceinline__ void loss_stage_heads(const LossArgs& a, float* s_dyn, float* s_sd, float* s_dsd) {
+    const int tid = threadIdx.x;
+    const bool gaussian = a.head == PPOAF_HEAD_GAUSSIAN_TANH;
+    const int prows = (a.pred_dim + kPB - 1) / kPB * kPB;
+    const int ldw = a.Ha + 4;
+    float* s_wa = s_dyn;                                             // [prows][ldw]
+    float* s_wc = s_wa + prows * ldw;                                // [Hc]
+    float* s_b = s_wc + a.Hc;                                        // [pred + 1]
+    {
+        const int qa = a.Ha / 4;
+        for (int t = tid; t < prows * qa; t += kStageThreads) {
+            const int row = t / qa, c4 = t - row * qa;
+            const float4 w = row < a.pred_dim ? __ldcg(reinterpret_cast<const float4*>(a.W_actor + int64_t(row) * a.Ha + 4 * c4))
+                                              : make_float4(0.f, 0.f, 0.f, 0.f);
+            *reinterpret_cast<float4*>(s_wa + row * ldw + 4 * c4) = w;
+        }
+        for (int t = tid; t < a.Hc / 4; t += kStageThreads)
+            *reinterpret_cast<float4*>(s_wc + 4 * t) = __ldcg(reinterpret_cast<const float4*>(a.W_critic + 4 * t));
+        if (tid < a.pred_dim) s_b[tid] = __ldcg(a.b_actor + tid);
+        if (tid == 0) s_b[a.pred_dim] = __ldcg(a.b_critic);
+        if (gaussian && tid < a.act_dim) {
+            const float ls = __ldcg(a.log_std + tid);
+            const float sp = softplus_torch(ls);
+            s_sd[tid] = fmaxf(sp, a.min_std);
+            const float sig = ls > 20.f ? 1.f : 1.f / (1.f + expf(-ls));
+            s_dsd[tid] = sp > a.min_std ? sig : (sp == a.min_std ? 0.5f * sig : 0.f);
+        }
+    }
+}
+
 // ---------------------------------------------------------------------------------------------------------
 // LOSS phase: one warp per sample, samples dealt round-robin over CTAs so that every SM holds 3-4 of a 512-row
 // minibatch.  Head layers, loss and the heads' dX as in ppo_loss_kernel<true> (loss.cu); the per-CTA partial sums are
@@ -577,27 +641,6 @@ __device__ __forceinline__ void loss_phase(const LossArgs& a, int cur, float* s_
     float* s_pred = s_b + ((a.pred_dim + 1 + 3) & ~3);               // [8 warps][kFusedPredLd]
     float* s_dpred = s_pred + (kStageThreads / 32) * kFusedPredLd;
 
-    // head weights of both networks (written by the ADAM phase of the previous step: L2 loads)
-    {
-        const int qa = a.Ha / 4;
-        for (int t = tid; t < prows * qa; t += kStageThreads) {
-            const int row = t / qa, c4 = t - row * qa;
-            const float4 w = row < a.pred_dim ? __ldcg(reinterpret_cast<const float4*>(a.W_actor + int64_t(row) * a.Ha + 4 * c4))
-                                              : make_float4(0.f, 0.f, 0.f, 0.f);
-            *reinterpret_cast<float4*>(s_wa + row * ldw + 4 * c4) = w;
-        }
-        for (int t = tid; t < a.Hc / 4; t += kStageThreads)
-            *reinterpret_cast<float4*>(s_wc + 4 * t) = __ldcg(reinterpret_cast<const float4*>(a.W_critic + 4 * t));
-        if (tid < a.pred_dim) s_b[tid] = __ldcg(a.b_actor + tid);
-        if (tid == 0) s_b[a.pred_dim] = __ldcg(a.b_critic);
-        if (gaussian && tid < a.act_dim) {
-            const float ls = __ldcg(a.log_std + tid);
-            const float sp = softplus_torch(ls);
-            s_sd[tid] = fmaxf(sp, a.min_std);
-            const float sig = ls > 20.f ? 1.f : 1.f / (1.f + expf(-ls));
-            s_dsd[tid] = sp > a.min_std ? sig : (sp == a.min_std ? 0.5f * sig : 0.f);
-        }
-    }
     float adv_mu = 0.f, adv_sd = 1.f, val_mu = 0.f, val_sd = 1.f;    // this minibatch's normalisation constants
     if (a.normalize_adv) { adv_mu = a.mb_adv_stats[2 * cur]; adv_sd = a.mb_adv_stats[2 * cur + 1]; }
     if (a.normalize_values) { val_mu = a.mb_val_stats[2 * cur]; val_sd = a.mb_val_stats[2 * cur + 1]; }
@@ -969,7 +1012,7 @@ __device__ __forceinline__ void gather_minibatch(const FusedPlan& P, int mb, int
 
 __global__ void __launch_bounds__(kFThreads, 1) ppo_fused_step_kernel(const __grid_constant__ FusedPlan P) {
     extern __shared__ uint8_t smem_raw[];
-    __shared__ __align__(8) uint64_t s_bars[4 * kFStages + 1];
+    __shared__ __align__(8) uint64_t s_bars[2 * kRawStages + 2 * kFStages + 1];
     __shared__ uint32_t s_tmem;
     __shared__ float s_sd[kMaxAct], s_dsd[kMaxAct];
     __shared__ double s_red[kStageThreads / 32][kPartialStride];
@@ -986,21 +1029,24 @@ __global__ void __launch_bounds__(kFThreads, 1) ppo_fused_step_kernel(const __gr
     }
     if (tid == 32) {
 #pragma unroll
-        for (int i = 0; i < kFStages; ++i) {
+        for (int i = 0; i < kRawStages; ++i) {
             mbar_init(&s_bars[i], kProdThreads);                   // raw_full: one cp.async arrival per thread of the MMA warpgroup
-            mbar_init(&s_bars[kFStages + i], kStageThreads / 32);  // raw_free: one arrival per converter warp
-            mbar_init(&s_bars[2 * kFStages + i], kStageThreads / 32);   // op_full
-            mbar_init(&s_bars[3 * kFStages + i], 4);               // mma_free: one tcgen05.commit per issuer warp
+            mbar_init(&s_bars[kRawStages + i], kStageThreads / 64);   // raw_free: one arrival per warp of the converter group that owns the chunk
         }
-        mbar_init(&s_bars[4 * kFStages], 4);                       // accumulators complete (all four issuers)
+#pragma unroll
+        for (int i = 0; i < kFStages; ++i) {
+            mbar_init(&s_bars[2 * kRawStages + i], kStageThreads / 64);          // op_full: likewise
+            mbar_init(&s_bars[2 * kRawStages + kFStages + i], 4);                // mma_free: one tcgen05.commit per issuer warp
+        }
+        mbar_init(&s_bars[2 * kRawStages + 2 * kFStages], 4);      // accumulators complete (all four issuers)
         asm volatile("fence.mbarrier_init.release.cluster;");
     }
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     __syncthreads();
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
     const uint32_t tmem = __shfl_sync(0xffffffffu, s_tmem, 0);
-    const TileBars tb{s_bars, s_bars + kFStages, s_bars + 2 * kFStages, s_bars + 3 * kFStages, s_bars + 4 * kFStages};
-    float* loss_smem = smem + kFStages * kStageFloatsV2;
+    const TileBars tb{s_bars, s_bars + kRawStages, s_bars + 2 * kRawStages, s_bars + 2 * kRawStages + kFStages, s_bars + 2 * kRawStages + 2 * kFStages};
+    float* loss_smem = smem + kTileSmemFloats;
 
     // launch-wide state, read before the first grid barrier (the counters are only written at the very end)
     uint32_t epoch = P.bar[kMaxGrid * kBarStride];
@@ -1051,9 +1097,10 @@ __global__ void __launch_bounds__(kFThreads, 1) ppo_fused_step_kernel(const __gr
                     if (slot >= 0) stp = P.stamps + (slot * kMaxPhases + ph) * 4;
                 }
                 if (stp) stp[0] = clock64();
+                const PhaseDesc d = P.ph[ph];
+                if (d.type == PH_LOSS) loss_stage_heads(P.loss, loss_smem, s_sd, s_dsd);
                 grid_sync(P.bar, ++epoch);
                 if (stp) stp[1] = clock64();
-                const PhaseDesc d = P.ph[ph];
                 if (ph == P.loss_finalize_phase && blockIdx.x == gridDim.x - 1) loss_finalize(P.loss, s_dsd, s_red, s_tot, s_sq);
                 if (d.type == PH_LOSS) {
                     loss_phase(P.loss, cur, loss_smem, s_sd, s_dsd, s_red, (stp && blockIdx.x == 0) ? P.stamps + 3 * kMaxPhases * 4 + ph * 32 : nullptr);
