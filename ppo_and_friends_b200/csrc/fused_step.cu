@@ -516,6 +516,7 @@ __device__ __forceinline__ void ftile(const GemmProblem& g, int tile, int64_t id
             }
         }
         asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+        if (dbg && j8 == 0) dbg[20] = clock64();
 #pragma unroll
         for (int pass = 0; pass < 2; ++pass) {
 #pragma unroll
@@ -527,6 +528,7 @@ __device__ __forceinline__ void ftile(const GemmProblem& g, int tile, int64_t id
                 }
             }
         }
+        if (dbg && j8 == 0) dbg[21] = clock64();
         if (m < g.M) {
 #pragma unroll
             for (int jj = 0; jj < 2; ++jj) {

@@ -50,7 +50,8 @@ for ph in range(nph):
         print(f"phase {ph} detail (loss: entry,staged,loads,heads,actor,dX,partials | adam: entry,sqloads,fold,scalars,compute,-,bar):", [int(x - r[0]) for x in r[:7]])
         continue
     print(f"tile detail phase {ph}: plan+first loads {r[1]-r[0]}, mainloop {r[2]-r[1]}, acc wait {r[3]-r[2]}, epilogue {r[28]-r[3]}")
-    print("   chunk 3 converter chain: raw ready", int(r[10]-r[0]), "lds+raw_free", int(r[29]-r[0]), "split", int(r[30]-r[0]), "mma_free ok", int(r[31]-r[0]), "sttm+wait", int(r[26]-r[0]), "proxy fence", int(r[27]-r[0]), "arrive", int(r[11]-r[0]))
+    print("   epilogue (first 8 columns): tmem loads", int(r[20]-r[3]), "sums", int(r[21]-r[20]), "rest (act, stores, 2nd column group)", int(r[28]-r[21]))
+    print("   chunk 4 converter chain: raw ready", int(r[10]-r[0]), "lds+raw_free", int(r[29]-r[0]), "split", int(r[30]-r[0]), "mma_free ok", int(r[31]-r[0]), "sttm+wait", int(r[26]-r[0]), "proxy fence", int(r[27]-r[0]), "arrive", int(r[11]-r[0]))
     print("   chunk (after free-wait, after arrive):", [(int(r[4+2*c]-r[0]), int(r[5+2*c]-r[0])) for c in range(12) if r[4+2*c]])
 
 m = np.array(buf[3 * nph * 4 + nph * 32: 3 * nph * 4 + 2 * nph * 32], dtype=np.int64).reshape(nph, 32)
