@@ -72,7 +72,7 @@ __device__ __forceinline__ uint32_t ld_acquire_gpu(const uint32_t* p) {
 
 // ctrl (local, zero-initialised): [0] epoch (barrier value of the last call), [2] grid-barrier "go" word, [3] ticket,
 // [4] error flag;
-// arrive (local, zero-initialised): one word per CTA for the grid barrier
+// arrive (local, zero-initialised): one word per CTA (grid barriers of the NVLS variant; the peer kernel counts on ctrl[2])
 __global__ void __launch_bounds__(kPeerThreads)
 peer_allreduce_adam_kernel(const PeerArgs pa, float* __restrict__ params, float* __restrict__ m, float* __restrict__ v,
                            int64_t n_actor, int64_t n_total, const double* __restrict__ hp,
@@ -148,25 +148,17 @@ peer_allreduce_adam_kernel(const PeerArgs pa, float* __restrict__ params, float*
     PEER_STAMP(3);
 
     // ---- 3. local grid barrier + fixed-order fold of the CTA partials ----
-    // no contended atomic (148 same-address atomics cost ~4000 clk): CTA b publishes `epoch` in its own arrival word,
-    // the threads of CTA 0 each poll one word and CTA 0 then releases a single "go" word that the others poll
+    // flat counter: every CTA adds one with a fire-and-forget red.release and polls the same word until it reads
+    // epoch * grid (the grid is the same for every call on these control words, so the count carries over like the epoch).
+    // Measured in the one-launch step kernel: 2.5 K clk, against 5.5 K for an arrival word per CTA
+    // gathered by CTA 0 plus a release word; an atomicAdd that RETURNS a value costs ~4000 clk at 148 CTAs.
     if (tid == 0) {
         partials[2 * blockIdx.x] = sa;
         partials[2 * blockIdx.x + 1] = sc;
-        asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(arrive + blockIdx.x), "r"(epoch) : "memory");
-    }
-    if (blockIdx.x == 0) {
-        if (tid < int(gridDim.x)) {
-            const long long t0 = clock64();
-            while (int32_t(ld_acquire_gpu(arrive + tid) - epoch) < 0) {
-                if (clock64() - t0 > kSpinLimit) { s_err = 1; break; }
-            }
-        }
-        __syncthreads();
-        if (tid == 0 && !s_err) asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(ctrl + 2), "r"(epoch) : "memory");
-    } else if (tid == 0) {
+        const uint32_t target = epoch * gridDim.x;
+        asm volatile("red.release.gpu.global.add.u32 [%0], 1;" ::"l"(ctrl + 2) : "memory");
         const long long t0 = clock64();
-        while (int32_t(ld_acquire_gpu(ctrl + 2) - epoch) < 0) {
+        while (int32_t(ld_acquire_gpu(ctrl + 2) - target) < 0) {
             if (clock64() - t0 > kSpinLimit) { s_err = 1; break; }
         }
     }
