@@ -563,6 +563,24 @@ def main():
                 f"({pk['source']} bf16 sustained) is the contract's denominator, fp32_peak_tflops_measured (cuBLAS SGEMM 4096^3, TF32 "
                 "off, measured in this run) the pipe it actually uses.  At B=512 the step is a chain of 8 dependent launches of "
                 "~40-270 MFLOP each: latency-bound, see DESIGN.md §3.3-3.4"}
+    if rank == 0 and world == 1 and os.environ.get("PPOAF_STEP", "chain") == "chain":
+        # the opt-in one-launch engine (csrc/fused_step.cu: TMA boxes + tcgen05 3xTF32 tiles with A in TMEM) on the same
+        # workload, same box, same timing rules: reported beside the default launch chain, not instead of it
+        os.environ["PPOAF_STEP"] = "fused"
+        pol._engine = None                                  # the engine is rebuilt (and re-reads PPOAF_STEP) on the next epoch
+        try:
+            ms_f = time_steps(lambda: hp.step(False), args.steps, args.warmup, flush)
+            used = bool(getattr(pol._engine, "fused", False))
+        finally:
+            os.environ["PPOAF_STEP"] = "chain"
+            pol._engine = None
+        line["step_engines"] = {
+            "chain (default): 8 PDL launches per minibatch step replayed from one CUDA graph per epoch, fp32 FFMA tiles":
+                {"value": value, "us_per_minibatch_step": us_per_mb},
+            "fused (PPOAF_STEP=fused): one persistent cooperative launch per epoch, TMA + tcgen05 kind::tf32 3xTF32, grid barriers":
+                ({"value": env_steps * args.steps / (ms_f / 1e3), "us_per_minibatch_step": 1e3 * (ms_f / args.steps) / mb_steps}
+                 if used else {"unsupported": "ppoaf_ppo_fused_supported() refused this configuration"}),
+            "note": "same pass, same timing rules, measured back to back in this process; DESIGN.md 3.4"}
     if rank == 0 and world == 1 and not args.no_microbench:
         mb = microbench_c2(pk)
         dom = max(mb["pieces"].items(), key=lambda kv: kv[1]["ms"])
