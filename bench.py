@@ -568,9 +568,12 @@ def main():
         # workload, same box, same timing rules: reported beside the default launch chain, not instead of it
         os.environ["PPOAF_STEP"] = "fused"
         pol._engine = None                                  # the engine is rebuilt (and re-reads PPOAF_STEP) on the next epoch
+        ms_f, used, fused_err = None, False, None
         try:
             ms_f = time_steps(lambda: hp.step(False), args.steps, args.warmup, flush)
             used = bool(getattr(pol._engine, "fused", False))
+        except Exception as exc:                            # the secondary engine must never take the headline line down
+            fused_err = f"{type(exc).__name__}: {exc}"[:300]
         finally:
             os.environ["PPOAF_STEP"] = "chain"
             pol._engine = None
@@ -579,7 +582,7 @@ def main():
                 {"value": value, "us_per_minibatch_step": us_per_mb},
             "fused (PPOAF_STEP=fused): one persistent cooperative launch per epoch, TMA + tcgen05 kind::tf32 3xTF32, grid barriers":
                 ({"value": env_steps * args.steps / (ms_f / 1e3), "us_per_minibatch_step": 1e3 * (ms_f / args.steps) / mb_steps}
-                 if used else {"unsupported": "ppoaf_ppo_fused_supported() refused this configuration"}),
+                 if used and ms_f else {"unavailable": fused_err or "ppoaf_ppo_fused_supported() refused this configuration"}),
             "note": "same pass, same timing rules, measured back to back in this process; DESIGN.md 3.4"}
     if rank == 0 and world == 1 and not args.no_microbench:
         mb = microbench_c2(pk)
