@@ -223,7 +223,7 @@ int ppoaf_ppo_minibatch_grads(const ppoaf_update_cfg* cfg, const ppoaf_update_bu
 int ppoaf_ppo_minibatch_apply(const ppoaf_update_cfg* cfg, const ppoaf_update_bufs* bufs, void* stream);
 
 /* The same minibatch step(s) as ONE persistent launch (fused_step.cu): n_steps consecutive minibatches of bufs->batch rows,
- * starting at *mb_cursor, each = forward (tcgen05 3xTF32 tiles) -> heads + loss -> backward -> clip + Adam, the phases
+ * starting at *mb_cursor, each = forward (TMA boxes + tcgen05 3xTF32 tiles) -> heads + loss -> backward -> clip + Adam, the phases
  * separated by grid barriers instead of launch boundaries; mb_cursor and adam_step advance by n_steps.  Replaces the loop
  * body of PPO._ppo_batch_train (ppo.py:2292-2468) for a whole epoch.  Supported when ppoaf_ppo_fused_supported(cfg) != 0
  * (equal depth >= 2 and activation of actor and critic, head layers fusable into the loss phase: hidden width <= 256 and
