@@ -12,6 +12,7 @@ epoch scalars.  Hyper-parameters live in a device block that is refreshed per ep
 schedulers keep working without re-capturing.
 """
 import ctypes as C
+import math
 import os
 from collections import OrderedDict
 
@@ -77,7 +78,11 @@ class UpdateEngine:
         self.hparams_host = torch.zeros(HP["COUNT"], dtype=torch.float64, pin_memory=True)
         self.hparams = torch.zeros(HP["COUNT"], dtype=torch.float64, device=dev)
         self.epoch_stats = torch.zeros(ST["COUNT"], dtype=torch.float64, device=dev)
-        self.epoch_stats_host = torch.zeros(ST["COUNT"], dtype=torch.float64, pin_memory=True)
+        # two pinned slots each for the epoch statistics and the permutation: with KL early stop disabled the trainer keeps
+        # one epoch in flight (train_policies), so epoch e + 1 is staged on the host while epoch e still reads its slot
+        self._stats_slots = [torch.zeros(ST["COUNT"], dtype=torch.float64, pin_memory=True) for _ in range(2)]
+        self._epoch_seq = 0
+        self._hp_uploaded = None
         self.mb_cursor = torch.zeros(1, dtype=torch.int32, device=dev)
         ws_bytes = load().ppoaf_update_workspace_bytes(C.byref(cfg), self.batch_size)
         self.workspace = torch.zeros(ws_bytes + 256, dtype=torch.uint8, device=dev)
@@ -101,19 +106,23 @@ class UpdateEngine:
 
     # -- hyper-parameters (read by the kernels every step) -----------------------------
     def refresh_hparams(self):
-        p, h = self.policy, self.hparams_host
-        h[HP["LR"]] = float(p.lr())
-        h[HP["ENTROPY_WEIGHT"]] = float(p.entropy_weight())
-        h[HP["SURR_CLIP"]] = float(p.surr_clip)
-        h[HP["GRAD_CLIP"]] = -1.0 if p.gradient_clip is None else float(p.gradient_clip)
-        h[HP["KL_WEIGHT"]] = float(p.kl_loss_weight)
-        h[HP["VF_CLIP"]] = -1.0 if p.vf_clip is None else float(p.vf_clip)
+        p = self.policy
         # Adam's own hyper-parameters come from the optimizer view (reference: optim.Adam(..., eps=1e-5),
         # policies/ppo_policy.py:341-345), so values restored by load_state_dict are honoured
         g = p.actor_optim.param_groups[0]
-        h[HP["BETA1"]], h[HP["BETA2"]], h[HP["ADAM_EPS"]] = float(g["betas"][0]), float(g["betas"][1]), float(g["eps"])
-        h[HP["INV_WORLD"]] = 1.0 / mpi_utils.get_num_procs()
+        vals = {"LR": float(p.lr()), "ENTROPY_WEIGHT": float(p.entropy_weight()), "SURR_CLIP": float(p.surr_clip),
+                "GRAD_CLIP": -1.0 if p.gradient_clip is None else float(p.gradient_clip),
+                "KL_WEIGHT": float(p.kl_loss_weight), "VF_CLIP": -1.0 if p.vf_clip is None else float(p.vf_clip),
+                "BETA1": float(g["betas"][0]), "BETA2": float(g["betas"][1]), "ADAM_EPS": float(g["eps"]),
+                "INV_WORLD": 1.0 / mpi_utils.get_num_procs()}
+        if vals == self._hp_uploaded:
+            return                       # unchanged since the last upload (also: the pinned staging block is not rewritten
+                                         # while an earlier asynchronous copy of it may still be queued)
+        h = self.hparams_host
+        for k, v in vals.items():
+            h[HP[k]] = v
         self.hparams.copy_(h, non_blocking=True)
+        self._hp_uploaded = vals
 
     # -- buffers struct for a given dataset / minibatch size ---------------------------------------------
     def _bufs(self, ds, rows, parity=0, fused=False):
@@ -173,7 +182,7 @@ class UpdateEngine:
         dev = self.device
         if self._perm_dev is None or self._perm_dev.numel() != n:
             self._perm_dev = torch.empty(n, dtype=torch.int64, device=dev)
-            self._perm_host = torch.empty(n, dtype=torch.int64, pin_memory=True)
+            self._perm_slots = [torch.empty(n, dtype=torch.int64, pin_memory=True) for _ in range(2)]
             self._mb_adv_stats = torch.zeros((n_mb, 2), dtype=torch.float32, device=dev)
             self._mb_val_stats = torch.zeros((n_mb, 2), dtype=torch.float32, device=dev)
             self._mb_val_triples = torch.zeros((n_mb, 3), dtype=torch.float64, device=dev)
@@ -270,6 +279,13 @@ class UpdateEngine:
 
     # -- one epoch = PPO._ppo_batch_train -------------------------------------------------------------------
     def run_epoch(self, ds):
+        """One epoch, synchronously: what `ppo_batch_train` needs (the caller decides about the next epoch from its result)."""
+        return self.finish_epoch(self.enqueue_epoch(ds, speculate=True))
+
+    def enqueue_epoch(self, ds, speculate=False):
+        """Enqueue one epoch on the current stream and return a token for `finish_epoch`.  Nothing here waits for the GPU:
+        the permutation and the statistics travel through pinned slots that alternate from epoch to epoch, so the caller
+        may stage the next epoch while this one runs (at most one epoch ahead: two slots)."""
         n = len(ds)
         n_mb = self._ensure_epoch_buffers(n)
         lib = load()
@@ -277,8 +293,11 @@ class UpdateEngine:
         perm = self._take_speculated_permutation(n)
         if perm is None:
             perm = draw_minibatch_permutation(n)
-        self._perm_host.copy_(perm)
-        self._perm_dev.copy_(self._perm_host, non_blocking=True)
+        slot = self._epoch_seq & 1
+        self._epoch_seq += 1
+        perm_host = self._perm_slots[slot]
+        perm_host.copy_(perm)
+        self._perm_dev.copy_(perm_host, non_blocking=True)
         check(lib.ppoaf_epoch_prepare(ptr(self._perm_dev), ptr(ds.advantages), ptr(ds.rewards_to_go), n, self.batch_size,
                                       ptr(self._mb_adv_stats), ptr(self._mb_val_triples), stream_ptr()),
               "ppoaf_epoch_prepare")
@@ -313,10 +332,18 @@ class UpdateEngine:
             for k in range(n_mb):
                 rows = min(self.batch_size, n - k * self.batch_size)
                 self._launch_step(ds, rows)
-        self.epoch_stats_host.copy_(self.epoch_stats, non_blocking=True)
-        self._speculate_next_permutation(n)                             # host work while the GPU runs the epoch
-        torch.cuda.current_stream(self.device).synchronize()            # the one host sync of the epoch
-        return self.epoch_stats_host.clone()
+        stats_host = self._stats_slots[slot]
+        stats_host.copy_(self.epoch_stats, non_blocking=True)
+        done = torch.cuda.Event()
+        done.record(torch.cuda.current_stream(self.device))
+        if speculate:
+            self._speculate_next_permutation(n)                         # host work while the GPU runs the epoch
+        return (stats_host, done)
+
+    def finish_epoch(self, token):
+        stats_host, done = token
+        done.synchronize()                                              # the one host wait of the epoch
+        return stats_host.clone()
 
 
 def _get_engine(ppo, policy_id, batch_size):
@@ -340,11 +367,20 @@ def ppo_batch_train(ppo, data_loader, policy_id):
         return
     ds = data_loader.dataset
     eng = _get_engine(ppo, policy_id, int(data_loader.batch_size))
-    st = eng.run_epoch(ds).numpy()
+    _record_epoch(ppo, policy_id, eng, eng.run_epoch(ds).numpy())
+
+
+def _check_epoch_flags(st):
     if st[ST["BAD_VALUE"]] > 0:
         mpi_utils.abort("ERROR: evaluate value or action prediction contains nan values!")
     if st[ST["BAD_RATIO"]] > 0:
         mpi_utils.abort("ERROR: ratios are nan or inf!")
+
+
+def _record_epoch(ppo, policy_id, eng, st):
+    """Epoch statistics -> status dictionary (ppo.py:2471-2485), one packed all-reduce when R > 1."""
+    policy = ppo.policies[policy_id]
+    _check_epoch_flags(st)
     peer_err = float(eng.peer.error_flag() != 0) if eng.peer is not None else 0.0
     sums = np.array([st[ST["COUNTER"]], st[ST["ENTROPY"]], st[ST["ACTOR_LOSS"]], st[ST["CRITIC_LOSS"]], st[ST["KL"]], peer_err])
     if mpi_utils.get_num_procs() > 1:                                   # ppo.py:2471-2475, one packed all-reduce
@@ -381,6 +417,9 @@ def train_policies(ppo):
         if policy.frozen:
             continue
         loader = _Loader(policy.dataset, ppo.batch_size)
+        if _no_early_stop(policy) and ppo.epochs_per_iter > 1 and os.environ.get("PPOAF_PIPELINE_EPOCHS", "1") == "1":
+            epochs_run[policy_id] = _train_policy_pipelined(ppo, loader, policy_id)
+            continue
         n_ep = 0
         for epoch_idx in range(ppo.epochs_per_iter):
             if epoch_idx > 0 and getattr(ppo, "recalc_advantages", False):
@@ -394,6 +433,35 @@ def train_policies(ppo):
                 break
         epochs_run[policy_id] = n_ep
     return epochs_run
+
+
+def _no_early_stop(policy):
+    """`kl avg > target_kl` (ppo.py:2222-2232) can never hold: no host decision separates two epochs."""
+    t = policy.target_kl
+    return t is None or (isinstance(t, (int, float)) and math.isinf(t) and t > 0)
+
+
+def _train_policy_pipelined(ppo, loader, policy_id):
+    """
+    All epochs of one policy with ONE epoch kept in flight: epoch e + 1 (permutation upload, per-epoch statistics kernels,
+    the captured minibatch graph) is enqueued before the host waits for epoch e, so the GPU never idles between epochs.
+    Only legal when nothing the host reads from epoch e decides about epoch e + 1, i.e. when KL early stop is disabled
+    (`_no_early_stop`); the operations and their order on the stream - and the draws from torch's CPU generator - are exactly
+    those of the epoch-by-epoch loop, so the results are bit-identical.  The status dictionary is written once, from the
+    last epoch (the reference overwrites it every epoch); the NaN / Inf checks of the earlier epochs run one epoch late.
+    """
+    policy = ppo.policies[policy_id]
+    eng = _get_engine(ppo, policy_id, int(loader.batch_size))
+    pending = None
+    for epoch_idx in range(ppo.epochs_per_iter):
+        if epoch_idx > 0 and getattr(ppo, "recalc_advantages", False):
+            loader.dataset.recalculate_advantages()
+        token = eng.enqueue_epoch(loader.dataset)
+        if pending is not None:
+            _check_epoch_flags(eng.finish_epoch(pending).numpy())
+        pending = token
+    _record_epoch(ppo, policy_id, eng, eng.finish_epoch(pending).numpy())
+    return ppo.epochs_per_iter
 
 
 class PPOUpdateState:

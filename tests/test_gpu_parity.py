@@ -603,6 +603,34 @@ def test_epoch_loop_kl_early_stop_and_lr_schedule():
     assert train_policies(state) == {"pol": 5}
 
 
+@pytest.mark.parametrize("recalc", [False, True])
+def test_pipelined_epochs_are_bit_identical_to_the_epoch_by_epoch_loop(recalc, monkeypatch):
+    """With KL early stop disabled (target_kl = inf) train_policies keeps one epoch in flight (no host wait between epochs).
+    Same stream order, same draws from the CPU generator: parameters, Adam state, dataset.values and the status dictionary
+    must equal the epoch-by-epoch loop bit for bit (ragged last minibatch, value normaliser and recalc_advantages included)."""
+    from ppo_and_friends_b200.ppo import PPOUpdateState, train_policies
+    from ppo_and_friends_b200.synthetic import make_rollout
+    out = {}
+    for mode in ("0", "1"):
+        monkeypatch.setenv("PPOAF_PIPELINE_EPOCHS", mode)
+        ro = make_rollout(seed=93, T=37, E=8, obs_dim=6, act_dim=2, max_ts_per_ep=8, obs_scale=False)
+        torch.manual_seed(5)
+        pol = make_policy(ro, act="tanh", actor_hidden=16, critic_hidden=24, lr=1e-3, target_kl=float("inf"))
+        ds = run_device_rollout(pol, ro)
+        state = PPOUpdateState({"pol": pol}, batch_size=64, epochs_per_iter=5, recalc_advantages=recalc)
+        torch.manual_seed(6)
+        for _ in range(2):                                   # two iterations: the slots and the speculation state carry over
+            assert train_policies(state) == {"pol": 5}
+        out[mode] = dict(params=pol.nets.flat_params.clone(), m=pol.nets.adam_m.clone(), v=pol.nets.adam_v.clone(),
+                         step=int(pol.nets.adam_step.item()), values=ds.values.clone(), adv=ds.advantages.clone(),
+                         status=dict(state.status_dict["pol"]), rng=torch.get_rng_state().clone(),
+                         vstats=state.value_normalizers["pol"].running_stats.state.clone())
+    a, b = out["0"], out["1"]
+    for k in ("params", "m", "v", "values", "adv", "rng", "vstats"):
+        assert torch.equal(a[k], b[k]), k
+    assert a["step"] == b["step"] and a["status"] == b["status"]
+
+
 # ----------------------------------------------------------------------------------------- §8f row 3: checkpoints
 def _golden_adam_state(g, prefix, keys):
     """torch.optim.Adam.state_dict() of the reference at `prefix` (the format policies/ppo_policy.py:1228-1247 saves)."""
