@@ -426,7 +426,7 @@ def train_policies(ppo):
                 loader.dataset.recalculate_advantages()
             ppo_batch_train(ppo, loader, policy_id)
             n_ep += 1
-            if ppo.status_dict[policy_id]["kl avg"] > policy.target_kl:
+            if policy.target_kl is not None and ppo.status_dict[policy_id]["kl avg"] > policy.target_kl:
                 if getattr(ppo, "verbose", False):
                     mpi_utils.rank_print("Target KL of {} has been reached. Ending early (after {} epochs)".format(
                         policy.target_kl, epoch_idx + 1))

@@ -243,6 +243,68 @@ def test_speculated_permutation_keeps_the_generator_protocol():
     assert UpdateEngine._take_speculated_permutation(eng, n + 1) is None
 
 
+def test_epoch_pipelining_order_and_when_it_is_allowed(monkeypatch):
+    """train_policies keeps ONE epoch in flight only when no host decision separates two epochs (target_kl = inf / None):
+    enqueue(0), enqueue(1), finish(0), enqueue(2), finish(1), ..., finish(last); the status dictionary comes from the last
+    epoch.  With a finite target_kl (the reference's default is 100) every epoch is finished before the next one starts."""
+    import types
+    import ppo_and_friends_b200.ppo as P
+    from ppo_and_friends_b200._lib import ST
+    log = []
+
+    class FakeEngine:
+        peer = None
+
+        def __init__(self):
+            self.k = 0
+
+        def enqueue_epoch(self, ds, speculate=False):
+            log.append(("enqueue", self.k, speculate))
+            self.k += 1
+            return self.k - 1
+
+        def finish_epoch(self, token):
+            log.append(("finish", token))
+            st = np.zeros(ST["COUNT"])
+            st[ST["COUNTER"]], st[ST["KL"]], st[ST["ACTOR_LOSS"]] = 2.0, 4.0 * (token + 1), 6.0
+            return torch.as_tensor(st)
+
+        def run_epoch(self, ds):
+            return self.finish_epoch(self.enqueue_epoch(ds, speculate=True))
+
+    eng = FakeEngine()
+    monkeypatch.setattr(P, "_get_engine", lambda ppo, pid, bs: eng)
+    recalcs = []
+    ds = types.SimpleNamespace(recalculate_advantages=lambda: recalcs.append(len(log)))
+    pol = types.SimpleNamespace(frozen=False, dataset=ds, target_kl=float("inf"), entropy_weight=lambda: 0.5,
+                                device="cpu")
+    ppo = types.SimpleNamespace(policies={"pol": pol}, batch_size=64, epochs_per_iter=4, recalc_advantages=True,
+                                status_dict={"pol": {}}, verbose=False)
+    assert P.train_policies(ppo) == {"pol": 4}
+    assert log == [("enqueue", 0, False), ("enqueue", 1, False), ("finish", 0), ("enqueue", 2, False), ("finish", 1),
+                   ("enqueue", 3, False), ("finish", 2), ("finish", 3)]
+    assert recalcs == [1, 3, 5]                        # before every epoch but the first, right before its enqueue
+    assert ppo.status_dict["pol"]["kl avg"] == 4.0 * 4 / 2.0 and ppo.status_dict["pol"]["actor loss"] == 3.0
+
+    # finite target: epoch by epoch, with the early stop decided from each epoch's own statistics
+    log.clear()
+    eng.k = 0
+    pol.target_kl = 100.0
+    assert P.train_policies(ppo) == {"pol": 4}
+    assert log == [x for k in range(4) for x in (("enqueue", k, True), ("finish", k))]
+    log.clear()
+    eng.k = 0
+    pol.target_kl = 3.0                                # kl avg of epoch 0 is 2, of epoch 1 is 4
+    assert P.train_policies(ppo) == {"pol": 2}
+    # the switch
+    log.clear()
+    eng.k = 0
+    pol.target_kl = None
+    monkeypatch.setenv("PPOAF_PIPELINE_EPOCHS", "0")
+    P.train_policies(ppo)
+    assert log[:3] == [("enqueue", 0, True), ("finish", 0), ("enqueue", 1, True)]
+
+
 def test_adam_view_state_dict_is_torch_adam_compatible():
     """The optimizer stand-in of the fused update reads and writes torch.optim.Adam state dicts (the format of the
     reference's `actor_optim_<rank>` checkpoint files, policies/ppo_policy.py:1228-1247).  Host-only: buffers on CPU."""
