@@ -170,6 +170,36 @@ def test_recalculate_advantages_matches_oracle():
 
 
 # ----------------------------------------------------------------------------------------- N1..N4
+def test_empty_inputs_through_the_c_abi():
+    """Zero-length inputs (a rank that collected nothing; an empty filter batch): every entry point that can legally see
+    them returns without launching and leaves its outputs alone; the batch moments of nothing are refused loudly
+    (numpy's mean of an empty batch is NaN + a warning in the reference: utils/stats.py:73-94 is never reached with it)."""
+    from ppo_and_friends_b200 import _lib, ops
+    dev = "cuda"
+    f32 = lambda *shape: torch.empty(shape, dtype=torch.float32, device=dev)
+    lib = _lib.load()
+    assert lib.ppoaf_gae_rtg_segscan(None, None, None, None, None, None, 0, 0, 0.99, 0.95, 1, None, None, None, 0,
+                                     _lib.stream_ptr()) == 0
+    adv, rtg = ops.gae_rtg_segscan(f32(0), f32(0), torch.empty(0, dtype=torch.uint8, device=dev),
+                                   torch.zeros(1, dtype=torch.int64, device=dev), f32(0), f32(0), 0.99, 0.95)
+    assert adv.numel() == 0 and rtg.numel() == 0
+    src = torch.arange(12, dtype=torch.float32, device=dev).reshape(3, 4)
+    out = ops.gather_rows(src, torch.empty(0, dtype=torch.int64, device=dev))
+    assert tuple(out.shape) == (0, 4)
+    state = torch.tensor([0.5, 2.0, 10.0], dtype=torch.float64, device=dev)
+    assert ops.normalize_clip(f32(0), state, 1).numel() == 0 and ops.denormalize(f32(0), state, 1).numel() == 0
+    before = state.clone()
+    ops.stats_merge(state, torch.empty(0, dtype=torch.float64, device=dev), 1)
+    assert torch.equal(state, before)
+    desc = _lib.MlpDesc.make([4, 8, 2], "tanh")
+    _, total = _lib.param_layout(desc)
+    y = ops.mlp_forward(desc, torch.zeros(total, dtype=torch.float32, device=dev), f32(0, 4))
+    assert tuple(y.shape) == (0, 2)
+    with pytest.raises(_lib.PpoafError):
+        ops.batch_moments(f32(0), 1)
+    torch.cuda.synchronize()
+
+
 @pytest.mark.parametrize("n,dim", [(1, 1), (50, 1), (4097, 1), (64, 5), (1000, 5), (7, 376), (5000, 376), (333, 18),
                                    (2048, 54), (100, 1030)])
 def test_batch_moments_and_merge_vs_oracle(n, dim):
