@@ -449,7 +449,7 @@ def run_reference_arm(args, w):
     R = max(int(args.gpus), 1)
     if reference_available():
         from oracle import ref_bench
-        steps = max(1, min(args.steps, 5))                      # bounded: a CPU step takes seconds (tens of seconds at R = 8)
+        steps = max(1, min(args.steps, 5 // R if R > 1 else 5))  # bounded: a CPU step takes ~8 s x R on a 16-core host (the ranks share the cores)
         wu = 1 if args.warmup > 0 else 0
         res = ref_bench.run(w, n_ranks=R, steps=steps, warmup=wu, epochs_timed=1)
         v, secs = res["value"], res["per_step_s"]

@@ -28,8 +28,13 @@ ROOT = os.path.dirname(HERE)
 
 def _worker(rank, world, port, w, steps, warmup, epochs_timed, total_threads, out_q):
     os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
-    for k in ("LOCAL_RANK", "GROUP_RANK", "ROLE_RANK", "TORCHELASTIC_RUN_ID"):
-        os.environ.pop(k, None)
+    # under torchrun the parent's environment carries the elastic agent's settings; TORCHELASTIC_USE_AGENT_STORE in particular
+    # makes every rank (rank 0 included) CONNECT to MASTER_PORT instead of serving the store there - with our own port nobody
+    # would serve it and the rendezvous would wait for its timeout
+    for k in list(os.environ):
+        if k.startswith("TORCHELASTIC_") or k in ("LOCAL_RANK", "GROUP_RANK", "ROLE_RANK", "LOCAL_WORLD_SIZE", "GROUP_WORLD_SIZE",
+                                                  "ROLE_WORLD_SIZE", "ROLE_NAME", "OMP_NUM_THREADS"):
+            os.environ.pop(k, None)
     import torch.distributed as dist
     torch.set_num_threads(max(int(total_threads), 1))
     if world > 1:
