@@ -184,3 +184,20 @@ def test_reference_cpu_arm_runs_with_two_ranks_over_gloo():
     assert one["kind"] == two["kind"] == "reference" and two["ranks"] == 2
     assert two["threads_per_rank"] <= max(one["threads_per_rank"] // 2, 1)          # set_torch_threads: threads / num_procs
     assert one["value"] > 0 and two["value"] > 0
+
+@pytest.mark.timeout(600)
+def test_reference_cpu_arm_under_a_torchrun_environment(monkeypatch):
+    """`bench.py --impl reference --gpus N` is launched by torchrun for N > 1: rank 0 spawns the gloo workers with the
+    elastic agent's environment inherited.  TORCHELASTIC_USE_AGENT_STORE would make the workers look for the agent's
+    store on THEIR port (nobody serves it: the rendezvous hangs), so the workers must shed that environment."""
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    sys.path.insert(0, root)
+    import bench
+    from oracle import ref_bench
+    for k, v in dict(TORCHELASTIC_USE_AGENT_STORE="True", TORCHELASTIC_RUN_ID="none", TORCHELASTIC_RESTART_COUNT="0",
+                     TORCHELASTIC_MAX_RESTARTS="0", LOCAL_RANK="0", RANK="0", WORLD_SIZE="2", LOCAL_WORLD_SIZE="2",
+                     GROUP_RANK="0", ROLE_RANK="0", MASTER_ADDR="127.0.0.1", MASTER_PORT="29799", OMP_NUM_THREADS="1").items():
+        monkeypatch.setenv(k, v)
+    w = dict(bench.WORKLOADS["c1"], ts=32, E=2, B=32, epochs=1)
+    two = ref_bench.run(w, n_ranks=2, steps=1, warmup=0, epochs_timed=1, port=29737)
+    assert two["ranks"] == 2 and two["value"] > 0
