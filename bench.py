@@ -15,7 +15,9 @@ One STEP = one pass of the hot path over one synthetic rollout shard per rank:
 from the pinned HOST ring (bulk H2D of the ring + segment table inside the timed region, D2H of the
 epoch statistics).  The GAE + normalisation microbench (BASELINE configs[1]: 2^22 timesteps, obs 376)
 runs on rank 0 in the same invocation and feeds `microbench` (with its own HBM roofline); `roofline` describes the
-dominant kernel of the timed region, the grouped GEMM launches of the minibatch step.
+dominant kernel of the timed region, the grouped GEMM launches of the minibatch step.  `step_engines` (N = 1) times the opt-in
+one-launch TMA + tcgen05 engine (PPOAF_STEP=fused) on the same workload right after the default launch chain.  With KL early
+stop disabled the trainer keeps one epoch in flight (no host wait between epochs; PPOAF_PIPELINE_EPOCHS=0 turns that off).
 The CPU baseline is the UNMODIFIED reference (oracle/_ref: a git-ignored copy made by oracle/build_ref.py in the
 build container, which travels to the GPU box like the built .so) timed on this box's host cores on a bounded
 sample; the oracle port (oracle/) is reported beside it.  `--impl reference` prints the reference arm on its own,
