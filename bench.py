@@ -557,7 +557,7 @@ def main():
         "fp32_peak_tflops_measured": fp32, "frac_of_fp32_peak": (upd_tflops / gemm_share / fp32) if fp32 else None,
         "kernel_share_of_step": gemm_share, "kernel_avg_launch_us": (gk["us"] / gk["count"]) if gk else None,
         "kernel_launches_per_step": (gk["count"]) if gk else None,
-        "share_source": "CUPTI activity records of one extra untimed step (torch.profiler)" if gk else "profiles/r01_launches_c4_summary.txt",
+        "share_source": "CUPTI activity records of one extra untimed step (torch.profiler)" if gk else "profiles/r02_launches_c4_summary.txt",
         "step_kernels": shares["kernels"] if shares else None,
         "note": f"dominant kernel of the timed region: {flops_step / 1e9:.2f} GFLOP per minibatch step (6*P_mm*B, SURVEY.md §8d) over "
                 f"{gemm_share:.2f} x the CUDA-event step time of {us_per_mb:.1f} us (the kernel's share comes from the committed "
